@@ -1,0 +1,154 @@
+/* ntm_b200.h -- C ABI of the B200-native NTM-cell hot path.
+ *
+ * Drop-in boundary for ONE path of JeffOwOSun/ntm-tracker: the NTMCell step
+ * unrolled over T timesteps for B independent sequences.  The reference has no
+ * FFI of its own (it is TensorFlow-1 graph code); each entry point below cites
+ * the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes only; every buffer is caller-owned
+ * DEVICE memory (fp32, contiguous, row-major) unless marked host; every call
+ * returns an ntm_b200_status and never throws; `stream` is a cudaStream_t passed
+ * as void*; calls are asynchronous on that stream and re-entrant (no global
+ * mutable state).  There is NO CPU fallback: on a machine without an sm_100
+ * device every compute entry point returns NTM_B200_ERR_NO_DEVICE.
+ */
+#ifndef NTM_B200_H_
+#define NTM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTM_B200_ABI_VERSION 1
+#define NTM_B200_MAX_LAYERS 16
+#define NTM_B200_MAX_READ_HEADS 4
+#define NTM_B200_MAX_WRITE_HEADS 3
+#define NTM_B200_MAX_SHIFT_RANGE 4
+
+typedef enum ntm_b200_status {
+  NTM_B200_OK = 0,
+  NTM_B200_ERR_BAD_SHAPE = 1,      /* reference: ValueError in _linear, ntm_cell.py:334-347 */
+  NTM_B200_ERR_BAD_SHIFT = 2,      /* reference: assert in circular_shift, ops.py:231 */
+  NTM_B200_ERR_NULL_POINTER = 3,
+  NTM_B200_ERR_UNSUPPORTED_HEADS = 4,
+  NTM_B200_ERR_TOO_LARGE = 5,      /* per-sequence state does not fit an 8-CTA cluster */
+  NTM_B200_ERR_WORKSPACE = 6,      /* workspace / packed buffer too small */
+  NTM_B200_ERR_NO_DEVICE = 7,      /* no CUDA device of compute capability 10.x */
+  NTM_B200_ERR_CUDA = 8,           /* a CUDA runtime call failed; see ntm_b200_last_cuda_error */
+  NTM_B200_ERR_DEVICE_TIMEOUT = 9  /* device-side grid barrier timed out (reported by ntm_b200_finish) */
+} ntm_b200_status;
+
+/* Constructor arguments of NTMCell (ntm_cell.py:18-20) plus the input width
+ * (the reference infers it from the `inputs` tensor, ntm_cell.py:103). */
+typedef struct ntm_b200_shape {
+  int32_t input_dim;             /* D: width of `inputs` */
+  int32_t output_dim;            /* O */
+  int32_t mem_size;              /* N */
+  int32_t mem_dim;               /* M */
+  int32_t shift_range;           /* S = 2*shift_range + 1 taps */
+  int32_t controller_hidden_size;/* C */
+  int32_t controller_num_layers; /* L */
+  int32_t write_head_size;       /* W */
+  int32_t read_head_size;        /* R */
+  int32_t write_first;           /* ntm_cell.py:212-215 */
+} ntm_b200_shape;
+
+/* Trainable variables in the reference's TensorFlow layout:
+ *   lstm_w[l]  ntm-cell/lstm-controller/cell_l/basic_lstm_cell/weights  [in_l + C, 4C]
+ *              in_0 = D + R*M (rows ordered x | read head-major | h), in_l = C
+ *   lstm_b[l]  .../biases [4C]            gate order i, j, f, o
+ *   addr_w/b   ntm-cell/addressing/{weights [C,P], biases [P]}  (_linear, ntm_cell.py:124)
+ *   out_w/b    ntm-cell/{weights [C,O], biases [O]}             (_linear, ntm_cell.py:220)  */
+typedef struct ntm_b200_weights {
+  const float* lstm_w[NTM_B200_MAX_LAYERS];
+  const float* lstm_b[NTM_B200_MAX_LAYERS];
+  const float* addr_w;
+  const float* addr_b;
+  const float* out_w;
+  const float* out_b;
+} ntm_b200_weights;
+
+/* The state dict {'M','w','read','controller_state'} (ntm_cell.py:223-228,
+ * 255-315).  Element [b] of each tensor starts at ptr + b*stride (in floats);
+ * a stride of 0 broadcasts one copy to every sequence (what zero_state's
+ * tf.stack([M]*batch) expresses, ntm_cell.py:296,301,306). */
+typedef struct ntm_b200_state {
+  float* M;                 /* [B, N, M] */
+  float* w;                 /* [B, R+W, N]  (read heads first) */
+  float* read;              /* [B, R, M] */
+  float* controller_state;  /* [B, 2*C*L]  per layer: c then h */
+  int64_t stride_M, stride_w, stride_read, stride_controller_state;
+} ntm_b200_state;
+
+/* Launch geometry the library will use for a shape (all fields outputs). */
+typedef struct ntm_b200_plan {
+  int32_t cluster_size;        /* CTAs sharing one sequence's memory rows (DSMEM) */
+  int32_t rows_per_cta;        /* memory rows resident in each CTA's shared memory */
+  int32_t sequences_resident;  /* sequences advanced concurrently per wave */
+  int32_t threads_per_cta;
+  int64_t smem_bytes_per_cta;
+  int64_t workspace_bytes;     /* for ntm_b200_forward_seq with this (B, T) */
+  int64_t packed_bytes;        /* for ntm_b200_pack_weights */
+  int64_t debug_floats_per_sequence; /* record size of the debug-tap buffer */
+} ntm_b200_plan;
+
+int32_t ntm_b200_abi_version(void);
+const char* ntm_b200_status_string(int32_t status);
+/* Text of the last CUDA error seen by this thread inside the library. */
+const char* ntm_b200_last_cuda_error(void);
+
+/* Shape validation + launch plan.  Pure host arithmetic: works without a GPU
+ * (assumes a B200: 148 SMs, 227 KiB shared memory per CTA) so the planner is
+ * unit-testable on CPU.  Replaces nothing in the reference (TF sizes its own
+ * kernels); it is the "smem/cluster plan" entry SURVEY.md s8b asks for. */
+int32_t ntm_b200_query(const ntm_b200_shape* shape, int64_t batch, int64_t steps,
+                       ntm_b200_plan* plan_out);
+
+/* One-time repacking of the variables into the kernel's layout (the
+ * [C, P+O] concatenation of the two _linear projections of ntm_cell.py:124,220).
+ * `packed` is a device buffer of plan.packed_bytes.  Must be re-run when the
+ * variables change.  Reference counterpart: tf.train.Saver.restore +
+ * variable creation in _linear (ntm_cell.py:354-369). */
+int32_t ntm_b200_pack_weights(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                              void* packed, int64_t packed_bytes, void* stream);
+
+/* LoopNTMTracker.__call__ (ntm_tracker_new.py:13-64): T cell steps for B
+ * sequences.  inputs [B,T,D] batch-major; logits/outputs [B,T,O] batch-major
+ * (`outputs` = softmax of logits, ntm_cell.py:221; may be NULL).
+ * state_in may alias state_out.  debug_taps (may be NULL) receives, for the LAST
+ * step, plan.debug_floats_per_sequence floats per sequence laid out as
+ * [k H*M | beta H | g H | sw H*S | gamma H | erase W*M | add W*M |
+ *  similarity H*N | w_content_focused H*N | w_gated H*N | w_conv H*N |
+ *  w_conv_powed H*N]  -- the taps of the reference's `debug` dict
+ * (ntm_cell.py:230-250) that are not derivable from the state. */
+int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                             const void* packed, int64_t batch, int64_t steps,
+                             const float* inputs, const ntm_b200_state* state_in,
+                             const ntm_b200_state* state_out, float* logits, float* outputs,
+                             float* debug_taps, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
+/* NTMCell.__call__ (ntm_cell.py:53-253): one step, inputs [B,D], logits/outputs
+ * [B,O].  The serve path's unit of work (test_tracker.py:284-299). */
+int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                      const void* packed, int64_t batch, const float* inputs,
+                      const ntm_b200_state* state_in, const ntm_b200_state* state_out,
+                      float* logits, float* outputs, float* debug_taps, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* Synchronise `stream` and report device-side failures of earlier calls that
+ * used `workspace` (grid-barrier timeout).  Optional: a caller that never
+ * checks still gets correct results when nothing failed. */
+int32_t ntm_b200_finish(void* workspace, void* stream);
+
+/* Number of kernel launches the library has issued in this process (for the
+ * bench harness' `gpu_launches` claim). */
+int64_t ntm_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTM_B200_H_ */

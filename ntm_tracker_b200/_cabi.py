@@ -1,0 +1,96 @@
+"""ctypes binding of include/ntm_b200.h (the C-ABI shared library).
+
+The library is the product; this file is the thin host-side stub a maintainer
+of the reference would add (INTEGRATION.md shows the same stub against the
+reference's files).  There is no fallback: if libntm_b200.so is missing or a
+call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+MAX_LAYERS = 16
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libntm_b200.so")
+
+OK = 0
+STATUS_VALUE_ERRORS = (1, 2, 4, 5)   # bad shape / bad shift / heads / too large -> ValueError
+
+
+class Shape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "input_dim", "output_dim", "mem_size", "mem_dim", "shift_range",
+        "controller_hidden_size", "controller_num_layers", "write_head_size",
+        "read_head_size", "write_first")]
+
+
+class Weights(C.Structure):
+    _fields_ = [("lstm_w", C.c_void_p * MAX_LAYERS), ("lstm_b", C.c_void_p * MAX_LAYERS),
+                ("addr_w", C.c_void_p), ("addr_b", C.c_void_p),
+                ("out_w", C.c_void_p), ("out_b", C.c_void_p)]
+
+
+class State(C.Structure):
+    _fields_ = [("M", C.c_void_p), ("w", C.c_void_p), ("read", C.c_void_p),
+                ("controller_state", C.c_void_p),
+                ("stride_M", C.c_int64), ("stride_w", C.c_int64), ("stride_read", C.c_int64),
+                ("stride_controller_state", C.c_int64)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("cluster_size", C.c_int32), ("rows_per_cta", C.c_int32),
+                ("sequences_resident", C.c_int32), ("threads_per_cta", C.c_int32),
+                ("smem_bytes_per_cta", C.c_int64), ("workspace_bytes", C.c_int64),
+                ("packed_bytes", C.c_int64), ("debug_floats_per_sequence", C.c_int64)]
+
+
+# every symbol include/ntm_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "ntm_b200_abi_version": (C.c_int32, []),
+    "ntm_b200_status_string": (C.c_char_p, [C.c_int32]),
+    "ntm_b200_last_cuda_error": (C.c_char_p, []),
+    "ntm_b200_query": (C.c_int32, [C.POINTER(Shape), C.c_int64, C.c_int64, C.POINTER(Plan)]),
+    "ntm_b200_pack_weights": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p,
+                                          C.c_int64, C.c_void_p]),
+    "ntm_b200_forward_seq": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p,
+                                         C.c_int64, C.c_int64, C.c_void_p, C.POINTER(State),
+                                         C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_void_p]),
+    "ntm_b200_step": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.POINTER(State), C.POINTER(State), C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ntm_b200_finish": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ntm_b200_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libntm_b200.so and bind every declared symbol (raises if absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "ntm_tracker_b200: %s not found -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status == OK:
+        return
+    lib = load()
+    msg = "%s: %s" % (what, lib.ntm_b200_status_string(status).decode())
+    if status == 8:
+        msg += " [%s]" % lib.ntm_b200_last_cuda_error().decode()
+    if status in STATUS_VALUE_ERRORS:
+        raise ValueError(msg)        # the reference raises ValueError on bad shapes
+    raise RuntimeError(msg)

@@ -1,0 +1,130 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ntm_b200.h declares,
+and its host-side logic (shape validation, launch planning) behaves.  No compute
+calls -- there is no GPU here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as entry
+from ntm_tracker_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return _cabi.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "ntm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(ntm_b200_[a-z_0-9]+)\s*\(", src))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    declared = header_symbols()
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_abi_version_and_status_strings(lib):
+    assert lib.ntm_b200_abi_version() == 1
+    for code in range(10):
+        assert len(lib.ntm_b200_status_string(code)) > 0
+    assert b"no CPU fallback" in lib.ntm_b200_status_string(7)
+
+
+def shape(**kw):
+    d = dict(input_dim=514, output_dim=2, mem_size=128, mem_dim=512, shift_range=1,
+             controller_hidden_size=200, controller_num_layers=1, write_head_size=1,
+             read_head_size=4, write_first=0)
+    d.update(kw)
+    return _cabi.Shape(**d)
+
+
+def query(lib, shp, B, T):
+    plan = _cabi.Plan()
+    st = lib.ntm_b200_query(C.byref(shp), B, T, C.byref(plan))
+    return st, plan
+
+
+def test_plan_tracker_config_uses_cta_pairs(lib):
+    """N*M*4 = 256 KiB > 227 KiB: the memory must be split over a 2-CTA cluster."""
+    st, plan = query(lib, shape(), 64, 32)
+    assert st == 0
+    assert plan.cluster_size == 2 and plan.rows_per_cta == 64
+    assert plan.sequences_resident == 64
+    assert plan.smem_bytes_per_cta <= 232448
+    st, plan = query(lib, shape(), 4096, 64)
+    assert plan.sequences_resident == 74          # 148 SMs / 2
+    assert plan.workspace_bytes >= 4096 * 64 * 800 * 4
+
+
+def test_plan_large_memory_uses_8_cta_clusters(lib):
+    st, plan = query(lib, shape(mem_size=1024, mem_dim=256), 512, 128)
+    assert st == 0 and plan.cluster_size == 8 and plan.rows_per_cta == 128
+    assert plan.smem_bytes_per_cta <= 232448
+
+
+def test_plan_copy_config_single_cta(lib):
+    st, plan = query(lib, shape(input_dim=4, output_dim=4, mem_dim=20, controller_hidden_size=100,
+                                read_head_size=1), 16, 20)
+    assert st == 0 and plan.cluster_size == 1 and plan.sequences_resident == 16
+    assert plan.debug_floats_per_sequence == 2 * 20 + 2 * 3 + 2 * 3 + 2 * 20 + 5 * 2 * 128
+
+
+@pytest.mark.parametrize("kw,code", [
+    (dict(mem_size=0), 1), (dict(controller_num_layers=17), 1), (dict(input_dim=0), 1),
+    (dict(shift_range=5), 2), (dict(mem_size=2, shift_range=1), 2),
+    (dict(read_head_size=5), 4), (dict(write_head_size=0), 4),
+    (dict(mem_size=8192, mem_dim=1024), 5),
+])
+def test_bad_shapes_are_rejected(lib, kw, code):
+    st, _ = query(lib, shape(**kw), 4, 4)
+    assert st == code
+
+
+def test_null_pointers_and_no_device(lib):
+    plan = _cabi.Plan()
+    assert lib.ntm_b200_query(None, 1, 1, C.byref(plan)) == 3
+    shp = shape()
+    import torch
+    if not torch.cuda.is_available():
+        # compute entry points must fail loudly without a device -- never fall back
+        w = _cabi.Weights()
+        buf = (C.c_char * 16)()
+        st = lib.ntm_b200_pack_weights(C.byref(shp), C.byref(w), buf, 1 << 40, None)
+        assert st == 7
+
+
+def test_python_boundary_mirrors_reference_errors():
+    from ntm_tracker_b200 import LoopNTMTracker, NTMCell
+    with pytest.raises(ValueError):
+        NTMCell(2, mem_size=2, shift_range=2)           # ops.py:231 assert
+    cell = NTMCell(4)                                     # the reference's defaults
+    assert (cell.mem_size, cell.mem_dim, cell.controller_num_layers,
+            cell.read_head_size, cell.write_head_size) == (128, 20, 10, 3, 3)
+    names = cell.variable_shapes(6)
+    assert names["ntm-tracker/ntm-cell/lstm-controller/cell_0/basic_lstm_cell/weights"] == (6 + 60 + 100, 400)
+    assert names["ntm-tracker/ntm-cell/lstm-controller/cell_9/basic_lstm_cell/weights"] == (200, 400)
+    assert names["ntm-tracker/ntm-cell/addressing/weights"] == (100, 6 * 20 + 6 * 3 + 6 * 3 + 2 * 20 * 3)
+    trk = LoopNTMTracker(5, 2, mem_size=16, mem_dim=8, controller_num_layers=1)
+    assert trk.sequence_length == 5 and trk.cell.output_dim == 2
+
+
+def test_variable_names_match_reference_source(golden_dir):
+    """The names the reference graph really creates were recorded by
+    oracle/make_golden.py (the shim raises on any unknown name); the oracle's
+    table and the package's table must be identical to each other."""
+    from ntm_tracker_b200 import NTMCell
+    from oracle import ntm_oracle as O
+    s = O.NTMShape(output_dim=3, input_dim=5, mem_size=16, mem_dim=8, controller_hidden_size=12,
+                   controller_num_layers=2, write_head_size=1, read_head_size=2)
+    cell = NTMCell(3, mem_size=16, mem_dim=8, controller_hidden_size=12, controller_num_layers=2,
+                   write_head_size=1, read_head_size=2)
+    assert cell.variable_shapes(5) == O.param_shapes(s)

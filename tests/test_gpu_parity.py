@@ -1,0 +1,250 @@
+"""GPU: parity of the CUDA path (through the C ABI, via the NTMCell /
+LoopNTMTracker boundary) with (a) the golden vectors recorded from the
+reference's own source and (b) the fp64 NumPy oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): max abs error <= 1e-4 on read vectors,
+weightings, memory and logits after T steps."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import ntm_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+CASES = ["small_r2w1_l2", "small_writefirst_s2", "c1_copy", "c2_tracker_b2t4", "defaults_r3w3_l3"]
+
+
+def kwargs_of(s):
+    return dict(mem_size=s.mem_size, mem_dim=s.mem_dim, shift_range=s.shift_range,
+                controller_hidden_size=s.controller_hidden_size,
+                controller_num_layers=s.controller_num_layers,
+                write_head_size=s.write_head_size, read_head_size=s.read_head_size,
+                write_first=s.write_first)
+
+
+def load_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    v = [int(t) for t in z["shape"]]
+    s = O.NTMShape(output_dim=v[0], input_dim=v[1], mem_size=v[2], mem_dim=v[3], shift_range=v[4],
+                   controller_hidden_size=v[5], controller_num_layers=v[6],
+                   write_head_size=v[7], read_head_size=v[8], write_first=bool(v[9]))
+    params = O.init_params(s, int(z["seed"]), 0.05, random_biases=bool(z["random_biases"]))
+    return z, s, params
+
+
+def make_tracker(s, params, T):
+    from ntm_tracker_b200 import LoopNTMTracker
+    trk = LoopNTMTracker(T, s.output_dim, **kwargs_of(s))
+    trk.cell.load_reference_weights(params)
+    return trk
+
+
+def maxerr(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_loop_matches_reference_golden(golden_dir, name):
+    z, s, params = load_case(golden_dir, name)
+    sub = int(z["m_stride"])
+    x = z["inputs"]
+    trk = make_tracker(s, params, x.shape[1])
+    out, logits = trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    st = trk.final_state
+    assert maxerr(to_np(logits), z["logits"]) <= TOL
+    assert maxerr(to_np(out), z["outputs"]) <= TOL
+    assert maxerr(to_np(st["w"]), z["final_w"]) <= TOL
+    assert maxerr(to_np(st["read"]), z["final_read"]) <= TOL
+    assert maxerr(to_np(st["controller_state"]), z["final_controller_state"]) <= TOL
+    assert maxerr(to_np(st["M"])[:, ::sub, ::sub], z["final_M"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["small_r2w1_l2", "small_writefirst_s2", "defaults_r3w3_l3", "c1_copy"])
+def test_stepwise_cell_and_debug_taps(golden_dir, name):
+    """The serve-path usage (test_tracker.py:284-299): one NTMCell call per step with
+    the state dict carried by the caller; the 19 debug taps at step 1."""
+    from ntm_tracker_b200 import NTMCell
+    z, s, params = load_case(golden_dir, name)
+    sub = int(z["m_stride"])
+    x = z["inputs"]
+    B, T, _ = x.shape
+    cell = NTMCell(s.output_dim, **kwargs_of(s))
+    cell.load_reference_weights(params)
+    cell.debug = True
+    state = cell.zero_state(B)
+    logits = []
+    dbg = None
+    for t in range(T):
+        out, lg, state, debug, M, w, read, cs = cell(torch.from_numpy(x[:, t]).cuda(), state)
+        assert M is state["M"] and w is state["w"] and read is state["read"]
+        logits.append(to_np(lg))
+        if t == min(1, T - 1):
+            dbg = {k: to_np(v) for k, v in debug.items()}
+    cell.finish()
+    assert maxerr(np.stack(logits, 1), z["logits"]) <= TOL
+    assert maxerr(to_np(state["M"])[:, ::sub, ::sub], z["final_M"]) <= TOL
+    assert maxerr(to_np(state["w"]), z["final_w"]) <= TOL
+    assert maxerr(to_np(state["read"]), z["final_read"]) <= TOL
+    assert len(dbg) == 19
+    for k, v in dbg.items():
+        got = v[:2]
+        if got.ndim >= 3 and got.shape[-1] == s.mem_dim and got.shape[-2] == s.mem_size:
+            got = got[..., ::sub, ::sub]
+        assert maxerr(np.squeeze(got), np.squeeze(z["dbg_" + k])) <= TOL, k
+
+
+def run_vs_oracle(s, B, T, seed, kind="tracker", scale=1.0):
+    params = O.init_params(s, seed, 0.05)
+    if kind == "tracker":
+        x = O.tracker_inputs(B, T, seed + 1, scale=scale, feat=s.input_dim - 2)
+    elif kind == "copy":
+        x = O.copy_task_inputs(B, T, s.input_dim - 1, seed + 1)
+    else:
+        x = np.random.RandomState(seed + 1).standard_normal((B, T, s.input_dim)).astype(np.float32)
+    trk = make_tracker(s, params, T)
+    out, logits = trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    ro, rl, rs = O.run_sequence(params, s, x)
+    st = trk.final_state
+    errs = {"logits": maxerr(to_np(logits), rl), "outputs": maxerr(to_np(out), ro)}
+    for k in ("M", "w", "read", "controller_state"):
+        errs[k] = maxerr(to_np(st[k]), rs[k])
+    return errs, trk, (out, logits)
+
+
+def test_c1_copy_full_config():
+    """BASELINE config 1 exactly: N128 M20 1R+1W LSTM100 B16 T20."""
+    kw, B, T = O.CONFIGS["c1_copy"]
+    errs, _, _ = run_vs_oracle(O.NTMShape(**kw), B, T, 21, kind="copy")
+    assert max(errs.values()) <= TOL, errs
+
+
+def test_c2_tracker_full_config():
+    """BASELINE config 2 exactly: N128 M512 4R+1W LSTM200 B64 T32 (2-CTA clusters)."""
+    kw, B, T = O.CONFIGS["c2_tracker"]
+    errs, _, _ = run_vs_oracle(O.NTMShape(**kw), B, T, 22)
+    assert max(errs.values()) <= TOL, errs
+
+
+def test_multi_wave_with_ragged_last_wave():
+    """More sequences than fit one wave (74 resident at the tracker shape) and a
+    last wave that is not full: 74 + 74 + 7."""
+    kw, _, _ = O.CONFIGS["c2_tracker"]
+    errs, _, _ = run_vs_oracle(O.NTMShape(**kw), 155, 3, 23)
+    assert max(errs.values()) <= TOL, errs
+
+
+def test_c4_large_memory_8cta_clusters():
+    """BASELINE config 4 shape (N1024 M256, 8-CTA clusters over DSMEM), reduced B, T."""
+    kw, _, _ = O.CONFIGS["c4_large"]
+    errs, _, _ = run_vs_oracle(O.NTMShape(**kw), 20, 4, 24)
+    assert max(errs.values()) <= TOL, errs
+
+
+@pytest.mark.parametrize("N,M,R,W,C,L,D,Odim,sr,wf", [
+    (7, 5, 1, 1, 3, 1, 1, 1, 1, False),        # odd, tiny, M not a multiple of 4
+    (33, 21, 4, 3, 9, 2, 3, 5, 2, True),       # ragged everything, max heads
+    (128, 130, 2, 2, 40, 1, 11, 2, 3, False),  # M spanning two chunk groups, S = 7
+    (260, 64, 3, 1, 24, 3, 8, 3, 1, True),     # N not a multiple of 32
+])
+def test_ragged_shapes(N, M, R, W, C, L, D, Odim, sr, wf):
+    s = O.NTMShape(output_dim=Odim, input_dim=D, mem_size=N, mem_dim=M, shift_range=sr,
+                   controller_hidden_size=C, controller_num_layers=L, write_head_size=W,
+                   read_head_size=R, write_first=wf)
+    errs, _, _ = run_vs_oracle(s, 6, 5, 31 + N, kind="normal")
+    assert max(errs.values()) <= TOL, errs
+
+
+def test_loop_equals_stepwise_and_is_deterministic():
+    """Size-independent properties: T steps in one call == T one-step calls with
+    the state carried by the caller; two identical calls are bit-identical."""
+    from ntm_tracker_b200 import NTMCell
+    kw, _, _ = O.CONFIGS["c2_tracker"]
+    s = O.NTMShape(**kw)
+    B, T = 9, 6
+    params = O.init_params(s, 41, 0.05)
+    x = torch.from_numpy(O.tracker_inputs(B, T, 42)).cuda()
+    trk = make_tracker(s, params, T)
+    out1, log1 = trk(x)
+    st1 = {k: v.clone() for k, v in trk.final_state.items()}
+    out2, log2 = trk(x)
+    trk.cell.finish()
+    assert torch.equal(log1, log2) and torch.equal(out1, out2)
+    for k in st1:
+        assert torch.equal(st1[k], trk.final_state[k]), k
+    cell = NTMCell(s.output_dim, **kwargs_of(s))
+    cell.load_reference_weights(params)
+    state = cell.zero_state(B)
+    logs = []
+    for t in range(T):
+        _, lg, state, _, _, _, _, _ = cell(x[:, t], state)
+        logs.append(lg)
+    cell.finish()
+    assert maxerr(to_np(torch.stack(logs, 1)), to_np(log1)) <= 1e-6
+    for k in st1:
+        assert maxerr(to_np(state[k]), to_np(st1[k])) <= 1e-6, k
+
+
+def test_sequences_are_independent():
+    """Sharding property: a sequence's result does not depend on
+    which other sequences share the batch -- the basis of the multi-GPU split."""
+    kw, _, _ = O.CONFIGS["c2_tracker"]
+    s = O.NTMShape(**kw)
+    params = O.init_params(s, 51, 0.05)
+    x = torch.from_numpy(O.tracker_inputs(12, 4, 52)).cuda()
+    trk = make_tracker(s, params, 4)
+    _, full = trk(x)
+    full = full.clone()
+    _, half = trk(x[6:])
+    trk.cell.finish()
+    assert maxerr(to_np(full[6:]), to_np(half)) <= 1e-5
+
+
+def test_weightings_structure():
+    """dnc/access_test.py-style structural checks: outputs are a simplex, the
+    weightings are non-negative and sum to just under 1 (the +1e-3 quirk)."""
+    kw, B, T = O.CONFIGS["c1_copy"]
+    errs, trk, (out, _) = run_vs_oracle(O.NTMShape(**kw), B, T, 61, kind="copy")
+    w = to_np(trk.final_state["w"])
+    assert (w >= 0).all() and (w.sum(-1) < 1.0).all() and (w.sum(-1) > 0.9).all()
+    np.testing.assert_allclose(to_np(out).sum(-1), 1.0, atol=1e-5)
+
+
+def test_host_inputs_round_trip():
+    """sess.run-like use: NumPy in, NumPy out (H2D / D2H inside the call)."""
+    kw, _, _ = O.CONFIGS["c1_copy"]
+    s = O.NTMShape(**kw)
+    params = O.init_params(s, 71, 0.05)
+    x = O.copy_task_inputs(4, 7, 3, 72)
+    trk = make_tracker(s, params, 7)
+    out, logits = trk(x)
+    assert isinstance(out, np.ndarray) and out.shape == (4, 7, 4)
+    _, rl, _ = O.run_sequence(params, s, x)
+    assert maxerr(logits, rl) <= TOL
+
+
+def test_degenerate_state_no_nan():
+    """All-zero memory / weightings / parameters: the 1e-12 floors keep everything finite."""
+    from ntm_tracker_b200 import NTMCell
+    s = O.NTMShape(output_dim=2, input_dim=3, mem_size=8, mem_dim=4, controller_hidden_size=6,
+                   controller_num_layers=1, write_head_size=1, read_head_size=1)
+    params = {k: np.zeros_like(v) for k, v in O.init_params(s, 0).items()}
+    cell = NTMCell(2, **kwargs_of(s))
+    cell.load_reference_weights(params)
+    st = cell.state_placeholder(2)
+    out, lg, st2, _, _, _, _, _ = cell(torch.zeros(2, 3).cuda(), st)
+    cell.finish()
+    for v in (out, lg, st2["M"], st2["w"], st2["read"], st2["controller_state"]):
+        assert torch.isfinite(v).all()
+    ro, rl, rs, _ = O.cell_step(params, s, np.zeros((2, 3)), {k: to_np(v) for k, v in st.items()})
+    assert maxerr(to_np(st2["w"]), rs["w"]) <= TOL
