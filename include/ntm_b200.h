@@ -144,6 +144,19 @@ int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weigh
  * checks still gets correct results when nothing failed. */
 int32_t ntm_b200_finish(void* workspace, void* stream);
 
+/* Measurement hooks for the bench harness: when enabled, ntm_b200_forward_seq
+ * brackets its two kernels (hoisted x-projection, persistent sequence kernel)
+ * with CUDA events on the caller's stream; after the stream has been
+ * synchronised ntm_b200_last_kernel_ms returns their device durations. */
+int32_t ntm_b200_set_profiling(int32_t enable);
+int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms);
+/* With profiling enabled the persistent kernel also accumulates, per CTA, SM-clock
+ * cycles spent in each phase of the timestep (16 int64 slots per CTA: 0/2/4/6 =
+ * phases A/B/C/D compute, 1/3/5/7 = the device-wide barrier after each, 8 =
+ * per-wave prologue, 9 = epilogue).  Copies max_ctas*16 counters to host `out`
+ * (synchronous; call after the stream has been synchronised). */
+int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_ctas);
+
 /* Number of kernel launches the library has issued in this process (for the
  * bench harness' `gpu_launches` claim). */
 int64_t ntm_b200_launch_count(void);

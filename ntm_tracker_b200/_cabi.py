@@ -59,6 +59,9 @@ SYMBOLS = {
                                   C.c_void_p, C.POINTER(State), C.POINTER(State), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ntm_b200_finish": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ntm_b200_set_profiling": (C.c_int32, [C.c_int32]),
+    "ntm_b200_last_kernel_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "ntm_b200_phase_cycles": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "ntm_b200_launch_count": (C.c_int64, []),
 }
 

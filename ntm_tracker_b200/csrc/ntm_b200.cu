@@ -43,7 +43,7 @@ namespace {
 constexpr int NT = 512;          // threads per CTA
 constexpr int NWARP = NT / 32;
 constexpr int RB = 4;            // memory rows per warp-group in pass 1
-constexpr int TBMAX = 24;        // max sequences per warp tile in the skinny GEMMs
+constexpr int TBMAX = 16;        // max sequences per warp tile in the skinny GEMMs
 constexpr int MAXL = NTM_B200_MAX_LAYERS;
 constexpr int SMAX = 2 * NTM_B200_MAX_SHIFT_RANGE + 1;
 constexpr int B200_SMS = 148;
@@ -80,6 +80,7 @@ struct KParams {
   float* partC;
   unsigned* ctr;
   int* err;
+  long long* prof;   // [ncta][16] per-phase cycle counters (measurement hook), or null
   // shared-memory carve-up, offsets in floats
   int oMs, oW0, oW1, oCn, oX0, oX1, oScr;
   int oSim, oWg, oK, oE, oA, oSm, oLog;
@@ -106,6 +107,15 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Phase-cycle accounting for the bench harness (thread 0 of each CTA; null = off).
+__device__ __forceinline__ void mark_slot(long long* row, long long& tmark, int slot) {
+  if (row != nullptr && threadIdx.x == 0) {
+    const long long now = clock64();
+    row[slot] += now - tmark;
+    tmark = now;
+  }
+}
+
 // Device-wide barrier over all CTAs of the (co-resident) grid.  Monotonic
 // counter, zeroed by the host before launch.  A bounded spin turns a lost CTA
 // into an error flag instead of a hung GPU.
@@ -113,8 +123,9 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, int* err, unsigned& epo
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += 1;
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    // release-add / acquire-poll: the release is cumulative over the CTA's writes ordered
+    // before it by the bar.sync above, so no separate (much slower) MEMBAR.SC is needed.
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     const unsigned target = epoch * nblk;
     long long t0 = clock64();
     unsigned spins = 0;
@@ -127,20 +138,56 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, int* err, unsigned& epo
         }
       }
     }
-    __threadfence();
   }
   __syncthreads();
 }
 
 // ------------------------------------------------ phases A / C: skinny GEMM --
 // part[ks][b][j] = sum_{k in slice ks} act[b][k] * Wt[k][j]   for all resident b.
-// CTA unit = (K-slice, group of JW 32-column tiles); the activation slice is
+// CTA unit = (K-slice, group of JW 64-column tiles); the activation slice is
 // staged once in shared memory ([Gpad][KW], read back as warp-broadcast float4
-// along k); each warp owns 32 columns (one per lane, coalesced weight reads
-// straight from L2) x TB sequences (register accumulators).
-__device__ __forceinline__ void gemm_phase(const GemmPlan& g, const float* act,
-                                           const float* __restrict__ Wt, float* part, int Gcur,
-                                           float* stage, int cta, int ncta) {
+// along k); each warp owns 64 columns (two per lane, coalesced float2 weight
+// reads straight from L2, each weight read once per CTA-unit row tile) x TB
+// sequences (register accumulators).  Summation order is k-ascending within a
+// slice and slice-ascending in the consumer, i.e. fixed: results are
+// bit-reproducible run to run.
+template <int TB>
+__device__ __forceinline__ void gemm_warp_tile(const float* __restrict__ wp, int ldw, const float* sp,
+                                               int KW, int kn, bool jok, float* pp, int NCs) {
+  float acc0[TB], acc1[TB];
+#pragma unroll
+  for (int i = 0; i < TB; ++i) { acc0[i] = 0.0f; acc1[i] = 0.0f; }
+  float2 w[4], nw[4];
+  auto loadw = [&](int kk, float2* d) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      d[q] = (jok && kk + q < kn) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)(kk + q) * ldw))
+                                  : make_float2(0.0f, 0.0f);
+  };
+  loadw(0, w);
+  for (int kk = 0; kk < KW; kk += 4) {
+    if (kk + 4 < KW) loadw(kk + 4, nw);
+#pragma unroll
+    for (int i = 0; i < TB; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(sp + i * KW + kk);
+      acc0[i] = fmaf(a.x, w[0].x, acc0[i]); acc1[i] = fmaf(a.x, w[0].y, acc1[i]);
+      acc0[i] = fmaf(a.y, w[1].x, acc0[i]); acc1[i] = fmaf(a.y, w[1].y, acc1[i]);
+      acc0[i] = fmaf(a.z, w[2].x, acc0[i]); acc1[i] = fmaf(a.z, w[2].y, acc1[i]);
+      acc0[i] = fmaf(a.w, w[3].x, acc0[i]); acc1[i] = fmaf(a.w, w[3].y, acc1[i]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = nw[q];
+  }
+  if (jok) {
+#pragma unroll
+    for (int i = 0; i < TB; ++i)
+      *reinterpret_cast<float2*>(pp + (size_t)i * NCs) = make_float2(acc0[i], acc1[i]);
+  }
+}
+
+__device__ __noinline__ void gemm_phase(const GemmPlan g, const float* act,
+                                        const float* __restrict__ Wt, float* part, int Gcur,
+                                        float* stage, int cta, int ncta) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwork = g.JW * g.NBT;
   for (int u = cta; u < g.units; u += ncta) {
@@ -156,43 +203,18 @@ __device__ __forceinline__ void gemm_phase(const GemmPlan& g, const float* act,
     }
     __syncthreads();
     const int jw = warp % g.JW, bt = warp / g.JW;
-    const int jbase = (jg * g.JW + jw) * 32;
+    const int jbase = (jg * g.JW + jw) * 64;
     if (warp < nwork && jbase < g.NC) {
-      const int j = jbase + lane;
-      const bool jok = j < g.NC;
-      float acc[TBMAX];
-#pragma unroll
-      for (int i = 0; i < TBMAX; ++i) acc[i] = 0.0f;
+      const int j = jbase + 2 * lane;
+      const bool jok = j < g.NC;          // NC and the row strides are even: a column pair is in or out together
       const float* wp = Wt + (size_t)k0 * g.ldw + (jok ? j : 0);
       const float* sp = stage + bt * g.TB * g.KW;
-      float w0, w1, w2, w3;
-      auto loadw = [&](int kk, float& a0, float& a1, float& a2, float& a3) {
-        a0 = (jok && kk + 0 < kn) ? __ldg(wp + (size_t)(kk + 0) * g.ldw) : 0.0f;
-        a1 = (jok && kk + 1 < kn) ? __ldg(wp + (size_t)(kk + 1) * g.ldw) : 0.0f;
-        a2 = (jok && kk + 2 < kn) ? __ldg(wp + (size_t)(kk + 2) * g.ldw) : 0.0f;
-        a3 = (jok && kk + 3 < kn) ? __ldg(wp + (size_t)(kk + 3) * g.ldw) : 0.0f;
-      };
-      loadw(0, w0, w1, w2, w3);
-      for (int kk = 0; kk < g.KW; kk += 4) {
-        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-        if (kk + 4 < g.KW) loadw(kk + 4, n0, n1, n2, n3);
-#pragma unroll
-        for (int i = 0; i < TBMAX; ++i) {
-          if (i < g.TB) {
-            const float4 a = *reinterpret_cast<const float4*>(sp + i * g.KW + kk);
-            acc[i] = fmaf(a.x, w0, acc[i]);
-            acc[i] = fmaf(a.y, w1, acc[i]);
-            acc[i] = fmaf(a.z, w2, acc[i]);
-            acc[i] = fmaf(a.w, w3, acc[i]);
-          }
-        }
-        w0 = n0; w1 = n1; w2 = n2; w3 = n3;
-      }
-      if (jok) {
-        float* pp = part + ((size_t)ks * g.Gpad + (size_t)bt * g.TB) * g.NCs + j;
-#pragma unroll
-        for (int i = 0; i < TBMAX; ++i)
-          if (i < g.TB) pp[(size_t)i * g.NCs] = acc[i];
+      float* pp = part + ((size_t)ks * g.Gpad + (size_t)bt * g.TB) * g.NCs + (jok ? j : 0);
+      switch (g.TB) {
+        case 4: gemm_warp_tile<4>(wp, g.ldw, sp, g.KW, kn, jok, pp, g.NCs); break;
+        case 8: gemm_warp_tile<8>(wp, g.ldw, sp, g.KW, kn, jok, pp, g.NCs); break;
+        case 12: gemm_warp_tile<12>(wp, g.ldw, sp, g.KW, kn, jok, pp, g.NCs); break;
+        default: gemm_warp_tile<16>(wp, g.ldw, sp, g.KW, kn, jok, pp, g.NCs); break;
       }
     }
   }
@@ -203,28 +225,41 @@ __device__ __forceinline__ void gemm_phase(const GemmPlan& g, const float* act,
 // h' = tanh(c')*sig(o).  z = hoisted x-projection (layer 0, bias folded in) or
 // bias (layers > 0) plus the K-slice partials of phase A in slice order.
 __device__ __forceinline__ void lstm_phase(const KParams& p, int l, int Gcur, int b0, int t,
-                                           int gtid, int gthreads) {
+                                           int cta, int ncta) {
   const GemmPlan& g = p.gA[l];
   const int C = p.C;
-  for (int i = gtid; i < Gcur * C; i += gthreads) {
-    const int b = i / C, u = i - b * C;
-    float z[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int col = q * C + u;
-      float v = (l == 0) ? __ldg(p.xw + ((size_t)(b0 + b) * p.T + t) * (size_t)(4 * C) + col)
-                         : __ldg(p.bA[l] + col);
-      for (int ks = 0; ks < g.KS; ++ks)
-        v += __ldcg(p.partA + ((size_t)ks * g.Gpad + b) * g.NCs + col);
-      z[q] = v;
+  // one lane per (sequence, unit, gate); the four gates of a unit sit in adjacent lanes
+  const int total = Gcur * C * 4;
+  const int chunk = ((total + ncta - 1) / ncta + 3) & ~3;
+  const int lo = cta * chunk, hi = min(total, lo + chunk);
+  const int KS = g.KS;
+  for (int base = lo; base < hi; base += NT) {
+    const int i = base + (int)threadIdx.x;
+    const bool ok = i < hi;
+    const int ii = ok ? i : lo;
+    const int q = ii & 3, bu = ii >> 2;
+    const int b = bu / C, u = bu - b * C;
+    const int col = q * C + u;
+    float v = (l == 0) ? __ldg(p.xw + ((size_t)(b0 + b) * p.T + t) * (size_t)(4 * C) + col)
+                       : __ldg(p.bA[l] + col);
+    const float* pa = p.partA + (size_t)b * g.NCs + col;
+    const size_t slab = (size_t)g.Gpad * g.NCs;
+#pragma unroll 8
+    for (int ks = 0; ks < KS; ++ks) v += __ldcg(pa + (size_t)ks * slab);
+    const unsigned lane = threadIdx.x & 31u, gl = lane & ~3u;
+    const float zi = __shfl_sync(0xffffffffu, v, gl + 0);
+    const float zj = __shfl_sync(0xffffffffu, v, gl + 1);
+    const float zf = __shfl_sync(0xffffffffu, v, gl + 2);
+    const float zo = __shfl_sync(0xffffffffu, v, gl + 3);
+    if (ok && q == 0) {
+      float* cp = p.cst + ((size_t)b * p.L + l) * C + u;
+      const float c_prev = __ldcg(cp);
+      const float c_new = c_prev * sigmoid_f(zf) + sigmoid_f(zi) * tanhf(zj);
+      const float h_new = tanhf(c_new) * sigmoid_f(zo);
+      *cp = c_new;
+      p.act[l][(size_t)b * p.actK[l] + (p.actK[l] - C) + u] = h_new;
+      if (l + 1 < p.L) p.act[l + 1][(size_t)b * p.actK[l + 1] + u] = h_new;
     }
-    float* cp = p.cst + ((size_t)b * p.L + l) * C + u;
-    const float c_prev = __ldcg(cp);
-    const float c_new = c_prev * sigmoid_f(z[2]) + sigmoid_f(z[0]) * tanhf(z[1]);
-    const float h_new = tanhf(c_new) * sigmoid_f(z[3]);
-    *cp = c_new;
-    p.act[l][(size_t)b * p.actK[l] + (p.actK[l] - C) + u] = h_new;
-    if (l + 1 < p.L) p.act[l + 1][(size_t)b * p.actK[l + 1] + u] = h_new;
   }
 }
 
@@ -260,7 +295,7 @@ __device__ __forceinline__ void finalize_colnorm(const KParams& p, cg::cluster_g
 template <int R, int W>
 __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& cluster, float* smem,
                                         int crank, int gslot, int bglob, int t, int row0, int nrows,
-                                        int& wcur, int xpar) {
+                                        int& wcur, int xpar, long long* prow, long long& tmark) {
   constexpr int H = R + W;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, M4 = p.M4, MC = p.MC, N = p.N, Npad = p.Npad, S = p.S;
@@ -287,8 +322,13 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   __syncthreads();
   for (int q = tid; q < p.PO; q += NT) {
     float v = __ldg(p.bC + q);
-    for (int ks = 0; ks < p.gC.KS; ++ks)
-      v += __ldcg(p.partC + ((size_t)ks * p.gC.Gpad + gslot) * p.gC.NCs + q);
+    {
+      const float* pc = p.partC + (size_t)gslot * p.gC.NCs + q;
+      const size_t slab = (size_t)p.gC.Gpad * p.gC.NCs;
+      const int KSc = p.gC.KS;
+#pragma unroll 8
+      for (int ks = 0; ks < KSc; ++ks) v += __ldcg(pc + (size_t)ks * slab);
+    }
     if (q < offBeta) {
       const int h = q / M, d = q - h * M;
       const float kv = tanhf(v);
@@ -357,6 +397,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
   }
   __syncthreads();
+  mark_slot(prow, tmark, 10);
   // kc[h][d] = k[h][d] * rs[h] * cn[d]   (in place)
   for (int i = tid; i < H * M4; i += NT) {
     const int h = i / M4, d = i - h * M4;
@@ -423,6 +464,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
   }
   cluster.sync();
+  mark_slot(prow, tmark, 11);
 
   // ---- addressing on the full [H][N] weighting, replicated in every CTA (ntm_cell.py:140-176) ----
   for (int h = warp; h < H; h += NWARP) {
@@ -462,7 +504,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
         idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
         conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
       }
-      const float pw = powf(conv, gamma);
+      const float pw = exp2f(gamma * log2f(conv));   // conv >= 0, gamma >= 1: == pow(conv, gamma), 0 -> 0
       sh[n] = pw;
       psum += pw;
       if (dbg) {
@@ -479,6 +521,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
   }
   __syncthreads();
+  mark_slot(prow, tmark, 12);
 
   // ---- pass 2: erase/add write, weighted read, next column norms (ntm_cell.py:193-215) ----
   {
@@ -549,6 +592,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
   }
   cluster.sync();
+  mark_slot(prow, tmark, 13);
 
   // ---- cluster reduction over DSMEM: column norms (all CTAs), read vector (split by rank) ----
   const int oX = xpar ? p.oX1 : p.oX0;
@@ -564,6 +608,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     if (last) p.dread[(size_t)bglob * p.dsread + i] = s;
   }
   wcur ^= 1;
+  mark_slot(prow, tmark, 14);
 }
 
 // ---------------------------------------------------------- the persistent kernel --
@@ -576,12 +621,14 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int crank = (int)cluster.block_rank();
   const int gslot = cta / p.CS;                    // cluster index = resident-sequence slot
-  const int gtid = cta * NT + tid, gthreads = ncta * NT;
   const int row0 = crank * p.NR;
   const int nrows = max(0, min(p.NR, p.N - row0));
   unsigned epoch = 0;
   float* Ms = smem + p.oMs;
   float* stage = smem + p.oScr;
+  long long tmark = clock64();
+  long long* prow = p.prof ? p.prof + (size_t)cta * 16 : nullptr;
+  auto mark = [&](int slot) { mark_slot(prow, tmark, slot); };
 
   for (int b0 = 0; b0 < p.B; b0 += p.G) {
     const int Gcur = min(p.G, p.B - b0);
@@ -619,21 +666,30 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
     if (active) finalize_colnorm(p, cluster, smem, p.oX1 + R * p.M4, smem + p.oCn);
     cluster.sync();   // peers finished reading oX1 before step 1 (xpar == 1) overwrites it
     grid_sync(p.ctr, p.err, epoch, ncta);
+    mark(8);
 
     for (int t = 0; t < p.T; ++t) {
       for (int l = 0; l < p.L; ++l) {
         gemm_phase(p.gA[l], p.act[l], p.wA[l], p.partA, Gcur, stage, cta, ncta);
+        mark(0);
         grid_sync(p.ctr, p.err, epoch, ncta);
-        lstm_phase(p, l, Gcur, b0, t, gtid, gthreads);
+        mark(1);
+        lstm_phase(p, l, Gcur, b0, t, cta, ncta);
+        mark(2);
         grid_sync(p.ctr, p.err, epoch, ncta);
+        mark(3);
       }
       gemm_phase(p.gC, p.act[p.L - 1] + (p.actK[p.L - 1] - p.C), p.wC, p.partC, Gcur, stage, cta, ncta);
+      mark(4);
       grid_sync(p.ctr, p.err, epoch, ncta);
+      mark(5);
       if (active) {
-        phase_d<R, W>(p, cluster, smem, crank, gslot, bglob, t, row0, nrows, wcur, xpar);
+        phase_d<R, W>(p, cluster, smem, crank, gslot, bglob, t, row0, nrows, wcur, xpar, prow, tmark);
         xpar ^= 1;
       }
+      mark(6);
       grid_sync(p.ctr, p.err, epoch, ncta);
+      mark(7);
     }
 
     // ---- epilogue: final state (ntm_cell.py:223-228) ----
@@ -654,6 +710,7 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
       }
     }
     cluster.sync();   // no CTA re-enters the prologue while a peer still reads its shared memory
+    mark(9);
   }
 }
 
@@ -679,6 +736,9 @@ __global__ void pack_ao_kernel(const float* __restrict__ aw, const float* __rest
 
 // --------------------------------------------------------------- host side --
 thread_local char g_cuda_err[256] = "";
+std::atomic<int> g_profiling{0};
+thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+thread_local bool g_ev_valid = false;
 std::atomic<long long> g_launches{0};
 
 int set_cuda_error(cudaError_t e, const char* where) {
@@ -776,8 +836,8 @@ GemmPlan plan_gemm(int K, int NC, int NCs, int ldw, int lda, int G, int ncta) {
   GemmPlan g{};
   g.K = K; g.NC = NC; g.NCs = NCs; g.ldw = ldw; g.lda = lda;
   const int G4 = round_up(std::max(G, 1), 4);
-  int best_nbt = 1, best_pad = 1 << 30;
-  for (int nbt = ceil_div(G4, TBMAX); nbt <= 8; ++nbt) {
+  int best_nbt = NWARP, best_pad = 1 << 30;
+  for (int nbt = ceil_div(G4, TBMAX); nbt <= NWARP; ++nbt) {
     const int tb = round_up(ceil_div(G4, nbt), 4);
     if (tb > TBMAX) continue;
     const int pad = nbt * tb;
@@ -787,8 +847,9 @@ GemmPlan plan_gemm(int K, int NC, int NCs, int ldw, int lda, int G, int ncta) {
   g.TB = round_up(ceil_div(G4, g.NBT), 4);
   g.Gpad = g.NBT * g.TB;
   g.JW = std::max(1, NWARP / g.NBT);
-  const int nj32 = ceil_div(NC, 32);
-  g.njg = ceil_div(nj32, g.JW);
+  const int nj64 = ceil_div(NC, 64);
+  g.JW = std::min(g.JW, nj64);
+  g.njg = ceil_div(nj64, g.JW);
   int KS = std::max(1, std::min(ncta / std::max(1, g.njg), ceil_div(K, 16)));
   int KW = round_up(ceil_div(K, KS), 4);
   const int kw_cap = std::max(4, (STAGE_BUDGET_BYTES / 4 / g.Gpad) / 4 * 4);
@@ -800,7 +861,7 @@ GemmPlan plan_gemm(int K, int NC, int NCs, int ldw, int lda, int G, int ncta) {
 }
 
 struct Workspace {
-  long long off_ctr, off_err, off_act[MAXL], off_cst, off_partA, off_partC, off_xw, total;
+  long long off_ctr, off_err, off_prof, off_act[MAXL], off_cst, off_partA, off_partC, off_xw, total;
 };
 
 // Workspace sized for the planner's upper bounds (Gmax resident sequences, a
@@ -813,6 +874,7 @@ void layout_workspace(const ntm_b200_shape* s, const HostPlan& hp, long long B, 
   auto take = [&](long long bytes) { long long r = o; o = align_up_ll(o + bytes, 256); return r; };
   ws->off_ctr = take(256);
   ws->off_err = take(256);
+  ws->off_prof = take(8ll * 16 * 1024);   // directly after ctr/err: zeroed by the same memset
   for (int l = 0; l < L; ++l) ws->off_act[l] = take(4ll * Gm * hp.actK[l]);
   ws->off_cst = take(4ll * Gm * L * C);
   // partial-slab sizes: maximum over every resident-sequence count the launch may end up with
@@ -989,6 +1051,12 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   const int G = (int)std::min<long long>(std::min(max_clusters, hp.Gmax), batch);
   const int ncta = G * hp.CS;
 
+  const bool prof = g_profiling.load() != 0;
+  if (prof) {
+    for (int i = 0; i < 3; ++i)
+      if (!g_ev[i] && (e = cudaEventCreate(&g_ev[i])) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+    cudaEventRecord(g_ev[0], stream);
+  }
   // hoisted x-projection: xw[b,t,:] = x[b,t,:] @ W_lstm0[0:D,:] + b_lstm0
   float* xw = reinterpret_cast<float*>(wsb + ws.off_xw);
   st = ntm_b200::launch_xproj(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
@@ -1025,13 +1093,15 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   p.partC = reinterpret_cast<float*>(wsb + ws.off_partC);
   p.ctr = reinterpret_cast<unsigned*>(wsb + ws.off_ctr);
   p.err = reinterpret_cast<int*>(wsb + ws.off_err);
+  p.prof = prof ? reinterpret_cast<long long*>(wsb + ws.off_prof) : nullptr;
   p.oMs = hp.oMs; p.oW0 = hp.oW0; p.oW1 = hp.oW1; p.oCn = hp.oCn; p.oX0 = hp.oX0; p.oX1 = hp.oX1;
   p.oScr = hp.oScr; p.oSim = hp.oSim; p.oWg = hp.oWg; p.oK = hp.oK; p.oE = hp.oE; p.oA = hp.oA;
   p.oSm = hp.oSm; p.oLog = hp.oLog;
 
-  e = cudaMemsetAsync(wsb + ws.off_ctr, 0, 512, stream);   // barrier counter + error flag
+  e = cudaMemsetAsync(wsb + ws.off_ctr, 0, 512 + 8 * 16 * 1024, stream);   // barrier counter, error flag, phase counters
   if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync");
 
+  if (prof) cudaEventRecord(g_ev[1], stream);
   cfg.gridDim = dim3(ncta);
   cfg.numAttrs = 2;   // cluster + cooperative (co-residency enforced by the driver)
   e = cudaLaunchKernelEx(&cfg, kern, p);
@@ -1044,6 +1114,10 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   }
   g_launches++;
   if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(ntm_seq_kernel)");
+  if (prof) {
+    cudaEventRecord(g_ev[2], stream);
+    g_ev_valid = true;
+  }
   return NTM_B200_OK;
 }
 
@@ -1054,6 +1128,30 @@ int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weigh
                       int64_t workspace_bytes, void* stream) {
   return ntm_b200_forward_seq(shape, weights, packed, batch, 1, inputs, state_in, state_out, logits,
                               outputs, debug_taps, workspace, workspace_bytes, stream);
+}
+
+int32_t ntm_b200_set_profiling(int32_t enable) {
+  g_profiling.store(enable ? 1 : 0);
+  return NTM_B200_OK;
+}
+
+int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms) {
+  if (!xproj_ms || !seq_kernel_ms) return NTM_B200_ERR_NULL_POINTER;
+  if (!g_ev_valid) return NTM_B200_ERR_BAD_SHAPE;
+  cudaError_t e = cudaEventElapsedTime(xproj_ms, g_ev[0], g_ev[1]);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaEventElapsedTime");
+  e = cudaEventElapsedTime(seq_kernel_ms, g_ev[1], g_ev[2]);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaEventElapsedTime");
+  return NTM_B200_OK;
+}
+
+int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_ctas) {
+  if (!workspace || !out) return NTM_B200_ERR_NULL_POINTER;
+  if (max_ctas < 1 || max_ctas > 1024) return NTM_B200_ERR_BAD_SHAPE;
+  cudaError_t e = cudaMemcpy(out, static_cast<const char*>(workspace) + 512, 8ll * 16 * max_ctas,
+                             cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaMemcpy(phase cycles)");
+  return NTM_B200_OK;
 }
 
 int32_t ntm_b200_finish(void* workspace, void* stream) {
