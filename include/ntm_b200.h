@@ -157,6 +157,11 @@ int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms);
  * (synchronous; call after the stream has been synchronised). */
 int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_ctas);
 
+/* Geometry of this thread's last ntm_b200_forward_seq launch: {tensor path used (0/1),
+ * resident sequences, CTAs, cluster size, K-slices and K-slice width of the layer-0 controller
+ * GEMM, K-slices and K-slice width of the head-parameter GEMM}. */
+int32_t ntm_b200_last_launch_info(int32_t* out8);
+
 /* Number of kernel launches the library has issued in this process (for the
  * bench harness' `gpu_launches` claim). */
 int64_t ntm_b200_launch_count(void);

@@ -62,6 +62,7 @@ SYMBOLS = {
     "ntm_b200_set_profiling": (C.c_int32, [C.c_int32]),
     "ntm_b200_last_kernel_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ntm_b200_phase_cycles": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "ntm_b200_last_launch_info": (C.c_int32, [C.POINTER(C.c_int32)]),
     "ntm_b200_launch_count": (C.c_int64, []),
 }
 
@@ -97,3 +98,11 @@ def check(status, what):
     if status in STATUS_VALUE_ERRORS:
         raise ValueError(msg)        # the reference raises ValueError on bad shapes
     raise RuntimeError(msg)
+
+
+def last_launch_info():
+    """{'tensor_path', 'sequences_resident', 'ctas', 'cluster_size', ...} of this thread's last launch."""
+    buf = (C.c_int32 * 8)()
+    check(load().ntm_b200_last_launch_info(buf), "last_launch_info")
+    keys = ("tensor_path", "sequences_resident", "ctas", "cluster_size", "ks_ctrl", "kw_ctrl", "ks_heads", "kw_heads")
+    return dict(zip(keys, list(buf)))

@@ -31,9 +31,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ntm_b200.h"
+#include "ntm_b200_umma.cuh"
 #include "ntm_b200_xproj.cuh"
 
 namespace cg = cooperative_groups;
@@ -53,6 +55,8 @@ constexpr int STAGE_BUDGET_BYTES = 44 * 1024;
 struct GemmPlan {
   int K, NC, NCs, ldw, lda;            // NCs: row stride of the partial slabs
   int KS, KW, JW, NBT, TB, Gpad, njg, units;
+  int tc;      // 1: tcgen05 path (128-column weight tiles resident in TMEM), 0: SIMT path
+  int tcol;    // tc: first TMEM column of this GEMM's weight tile (KW/2 "hi" columns, then KW/2 "lo")
 };
 
 struct KParams {
@@ -84,6 +88,8 @@ struct KParams {
   // shared-memory carve-up, offsets in floats
   int oMs, oW0, oW1, oCn, oX0, oX1, oScr;
   int oSim, oWg, oK, oE, oA, oSm, oLog;
+  int oTc;       // 4 floats: mbarrier (8 B) + TMEM base address (4 B)
+  int use_tc;    // any GEMM on the tensor path -> allocate TMEM
 };
 
 // ------------------------------------------------------------------ helpers --
@@ -218,6 +224,128 @@ __device__ __noinline__ void gemm_phase(const GemmPlan g, const float* act,
       }
     }
   }
+}
+
+// ------------------------------------- phases A / C on the tensor cores (tcgen05) --
+// Same contract as gemm_phase (K-slice partial slabs part[ks][b][j]), but each CTA owns ONE
+// unit = (128-column tile, K-slice) whose weights stay RESIDENT IN TENSOR MEMORY for the whole
+// kernel as a bf16 "hi" + bf16 "lo" pair (a = hi + lo to ~2^-18): loaded once by
+// tc_load_weights, used as the A operand of tcgen05.mma (A from TMEM).  Per timestep only the
+// activations move: fp32 [b][k] from L2 -> split into bf16 hi/lo -> K-major SWIZZLE_128B tiles
+// in shared memory (B operand, N = sequences); D[128 cols][N] += Whi*Bhi + Whi*Blo + Wlo*Bhi
+// accumulates in TMEM (fp32), then goes straight to the partial slab.
+__device__ __forceinline__ void tc_load_weights(const GemmPlan& g, const float* __restrict__ Wt, uint32_t tmem,
+                                                int cta) {
+  using namespace ntm_b200::umma;
+  if (!g.tc || cta >= g.units) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = cta / g.njg, tile = cta - ks * g.njg;
+  const int k0 = ks * g.KW;
+  const int j = tile * 128 + 32 * (warp & 3) + lane;      // weight column = TMEM lane
+  const bool jok = j < g.NC;
+  const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+  const int kq = g.KW / 16;                               // 16-k groups in the slice
+  for (int q = warp >> 2; q < kq; q += NWARP / 4) {       // the 4 warps sharing a lane quarter split k
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + q * 16 + 2 * e;
+      const float v0 = (jok && k < g.K) ? __ldg(Wt + (size_t)k * g.ldw + j) : 0.0f;
+      const float v1 = (jok && k + 1 < g.K) ? __ldg(Wt + (size_t)(k + 1) * g.ldw + j) : 0.0f;
+      split_pack_bf16(v0, v1, hi[e], lo[e]);
+    }
+    tmem_st_x8(tmem + lane_addr + g.tcol + q * 8, hi);
+    tmem_st_x8(tmem + lane_addr + g.tcol + g.KW / 2 + q * 8, lo);
+  }
+  tmem_wait_st();
+}
+
+__device__ __noinline__ void gemm_phase_tc(const GemmPlan g, const float* act, float* part, int Gcur,
+                                           uint8_t* stage, uint32_t tmem, uint64_t* mbar, uint32_t& mbar_uses,
+                                           int cta) {
+  using namespace ntm_b200::umma;
+  if (cta >= g.units) return;                              // CTA-uniform
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ks = cta / g.njg, tile = cta - ks * g.njg;
+  const int k0 = ks * g.KW;
+  const int N = g.Gpad;                                    // MMA N (multiple of 16)
+  const int katoms = (g.KW + 63) >> 6;
+  uint8_t* sBhi = stage;
+  uint8_t* sBlo = stage + (size_t)katoms * N * 128;
+  // ---- stage activations: one 16-byte chunk (8 consecutive k) per thread-iteration ----
+  const int cpr = katoms * 8;                              // chunks per row
+  const bool vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(act) & 15) == 0);
+  for (int i = tid; i < N * cpr; i += NT) {
+    const int b = i / cpr, c = i - b * cpr;
+    const int kk = c * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+    if (b < Gcur && kk < g.KW) {
+      const float* src = act + (size_t)b * g.lda + k0 + kk;
+      if (vec && k0 + kk + 8 <= g.K) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+        const float4 c4 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (k0 + kk + e < g.K) v[e] = __ldcg(src + e);
+      }
+    }
+    uint4 h, l;
+    split_pack_bf16(v[0], v[1], h.x, l.x);
+    split_pack_bf16(v[2], v[3], h.y, l.y);
+    split_pack_bf16(v[4], v[5], h.z, l.z);
+    split_pack_bf16(v[6], v[7], h.w, l.w);
+    const uint32_t off = sw128_offset(b, kk, N);
+    *reinterpret_cast<uint4*>(sBhi + off) = h;
+    *reinterpret_cast<uint4*>(sBlo + off) = l;
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  // ---- MMA issue: one elected thread ----
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, N);
+      uint32_t accum = 0;
+      for (int kk = 0; kk < g.KW; kk += 16) {
+        const int atom = kk >> 6, kin = kk & 63;
+        const uint64_t dhi = make_sw128_desc(sBhi + (size_t)atom * N * 128 + kin * 2);
+        const uint64_t dlo = make_sw128_desc(sBlo + (size_t)atom * N * 128 + kin * 2);
+        const uint32_t ahi = tmem + g.tcol + kk / 2, alo = ahi + g.KW / 2;
+        mma_ts(tmem, ahi, dhi, idesc, accum);
+        accum = 1;
+        mma_ts(tmem, ahi, dlo, idesc, accum);
+        mma_ts(tmem, alo, dhi, idesc, accum);
+      }
+      mma_commit(mbar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(mbar, mbar_uses & 1u);
+  mbar_uses += 1;
+  tcgen05_fence_after();
+  // ---- epilogue: accumulator rows (weight columns) -> partial slab, coalesced over j ----
+  {
+    const int j = tile * 128 + 32 * (warp & 3) + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const int nq = N / 4;                                  // accumulator columns (sequences) per warp quarter
+    const int bq0 = (warp >> 2) * nq;
+    float* pp = part + ((size_t)ks * g.Gpad) * g.NCs + j;
+    for (int c = 0; c < nq; c += 4) {
+      uint32_t v[4];
+      tmem_ld_x4(tmem + lane_addr + bq0 + c, v);
+      tmem_wait_ld();
+      if (j < g.NC) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pp[(size_t)(bq0 + c + e) * g.NCs] = __uint_as_float(v[e]);
+      }
+    }
+  }
+  tcgen05_fence_before();   // order the TMEM reads before the next phase's MMAs (after the grid barrier)
 }
 
 // ------------------------------------------------------- phase B: LSTM gates --
@@ -626,6 +754,25 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
   unsigned epoch = 0;
   float* Ms = smem + p.oMs;
   float* stage = smem + p.oScr;
+  // ---- tensor path: TMEM allocation + one-time load of this CTA's weight tiles ----
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + p.oTc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.oTc + 2);
+  uint32_t tmem = 0, mbar_uses = 0;
+  uint8_t* stage_tc = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(stage) + 1023) & ~static_cast<uintptr_t>(1023));
+  if (p.use_tc) {
+    if (tid < 32) ntm_b200::umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 32) ntm_b200::umma::mbar_init(mbar, 1);
+    ntm_b200::umma::tcgen05_fence_before();
+    __syncthreads();
+    ntm_b200::umma::tcgen05_fence_after();
+    tmem = *tmem_slot;
+    for (int l = 0; l < p.L; ++l) tc_load_weights(p.gA[l], p.wA[l], tmem, cta);
+    tc_load_weights(p.gC, p.wC, tmem, cta);
+    ntm_b200::umma::tcgen05_fence_before();
+    __syncthreads();
+    ntm_b200::umma::tcgen05_fence_after();
+  }
   long long tmark = clock64();
   long long* prow = p.prof ? p.prof + (size_t)cta * 16 : nullptr;
   auto mark = [&](int slot) { mark_slot(prow, tmark, slot); };
@@ -670,7 +817,8 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
 
     for (int t = 0; t < p.T; ++t) {
       for (int l = 0; l < p.L; ++l) {
-        gemm_phase(p.gA[l], p.act[l], p.wA[l], p.partA, Gcur, stage, cta, ncta);
+        if (p.gA[l].tc) gemm_phase_tc(p.gA[l], p.act[l], p.partA, Gcur, stage_tc, tmem, mbar, mbar_uses, cta);
+        else gemm_phase(p.gA[l], p.act[l], p.wA[l], p.partA, Gcur, stage, cta, ncta);
         mark(0);
         grid_sync(p.ctr, p.err, epoch, ncta);
         mark(1);
@@ -679,7 +827,8 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
         grid_sync(p.ctr, p.err, epoch, ncta);
         mark(3);
       }
-      gemm_phase(p.gC, p.act[p.L - 1] + (p.actK[p.L - 1] - p.C), p.wC, p.partC, Gcur, stage, cta, ncta);
+      if (p.gC.tc) gemm_phase_tc(p.gC, p.act[p.L - 1] + (p.actK[p.L - 1] - p.C), p.partC, Gcur, stage_tc, tmem, mbar, mbar_uses, cta);
+      else gemm_phase(p.gC, p.act[p.L - 1] + (p.actK[p.L - 1] - p.C), p.wC, p.partC, Gcur, stage, cta, ncta);
       mark(4);
       grid_sync(p.ctr, p.err, epoch, ncta);
       mark(5);
@@ -712,6 +861,11 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
     cluster.sync();   // no CTA re-enters the prologue while a peer still reads its shared memory
     mark(9);
   }
+  if (p.use_tc) {
+    ntm_b200::umma::tcgen05_fence_before();
+    __syncthreads();
+    if (tid < 32) ntm_b200::umma::tmem_dealloc(tmem, 512);
+  }
 }
 
 // ------------------------------------------------------------------ packing --
@@ -739,6 +893,7 @@ thread_local char g_cuda_err[256] = "";
 std::atomic<int> g_profiling{0};
 thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
 thread_local bool g_ev_valid = false;
+thread_local int g_last_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 std::atomic<long long> g_launches{0};
 
 int set_cuda_error(cudaError_t e, const char* where) {
@@ -754,7 +909,7 @@ struct HostPlan {
   int H, S, P, PO, PO4, M4, MC, Npad;
   int CS, NR, Gmax;
   int smem_floats;
-  int oMs, oW0, oW1, oCn, oX0, oX1, oScr, oSim, oWg, oK, oE, oA, oSm, oLog;
+  int oMs, oW0, oW1, oCn, oX0, oX1, oScr, oSim, oWg, oK, oE, oA, oSm, oLog, oTc;
   int scr_floats;
   int actK[MAXL];
   long long packed_bytes, debug_floats;
@@ -798,6 +953,7 @@ long long layout_for(const ntm_b200_shape* s, int CS, HostPlan* hp) {
   hp->oCn = take(hp->M4);
   hp->oX0 = take((R + 1) * hp->M4);
   hp->oX1 = take((R + 1) * hp->M4);
+  hp->oTc = take(4);
   hp->oScr = o;
   // phase-D temporaries inside the scratch union
   int d = o;
@@ -860,6 +1016,52 @@ GemmPlan plan_gemm(int K, int NC, int NCs, int ldw, int lda, int G, int ncta) {
   return g;
 }
 
+// Tensor-path plan: one unit (128-column tile x K-slice) per CTA, weights resident in TMEM.
+bool plan_gemm_tc(int K, int NC, int NCs, int ldw, int lda, int G, int ncta, int tcol, int scr_bytes,
+                  GemmPlan* out) {
+  GemmPlan g{};
+  g.K = K; g.NC = NC; g.NCs = NCs; g.ldw = ldw; g.lda = lda;
+  g.tc = 1;
+  g.tcol = tcol;
+  g.Gpad = round_up(std::max(G, 1), 16);
+  if (g.Gpad > 256) return false;
+  const int tiles = ceil_div(NC, 128);
+  if (tiles > ncta) return false;
+  int KS = std::max(1, std::min(ncta / tiles, ceil_div(K, 16)));
+  if (const char* e = getenv("NTM_B200_TC_MAX_KS")) KS = std::max(1, std::min(KS, atoi(e)));
+  const int KW = round_up(ceil_div(K, KS), 16);
+  KS = ceil_div(K, KW);
+  const int katoms = ceil_div(KW, 64);
+  if (2 * g.Gpad * katoms * 128 + 1024 > scr_bytes) return false;
+  g.KW = KW; g.KS = KS; g.njg = tiles; g.units = KS * tiles;
+  *out = g;
+  return true;
+}
+
+// All GEMM plans of one launch.  The tensor path is used when every GEMM's weight tile fits the
+// 512 TMEM columns next to the accumulator (else the SIMT path, e.g. for small grids).
+void choose_plans(const ntm_b200_shape* s, const HostPlan& hp, int G, int ncta, bool allow_tc,
+                  GemmPlan* gA, GemmPlan* gC, int* use_tc) {
+  const int C = s->controller_hidden_size, L = s->controller_num_layers;
+  const int scr_bytes = 4 * hp.scr_floats;
+  bool tc = allow_tc && getenv("NTM_B200_DISABLE_TC") == nullptr;
+  if (tc) {
+    int col = round_up(round_up(std::max(G, 1), 16), 32);     // accumulator columns first
+    for (int l = 0; l < L && tc; ++l) {
+      tc = plan_gemm_tc(hp.actK[l], 4 * C, 4 * C, 4 * C, hp.actK[l], G, ncta, col, scr_bytes, &gA[l]);
+      if (tc) col += gA[l].KW;
+    }
+    if (tc) tc = plan_gemm_tc(C, hp.PO, hp.PO4, hp.PO4, hp.actK[L - 1], G, ncta, col, scr_bytes, gC);
+    if (tc) col += gC->KW;
+    if (col > 512) tc = false;
+  }
+  if (!tc) {
+    for (int l = 0; l < L; ++l) gA[l] = plan_gemm(hp.actK[l], 4 * C, 4 * C, 4 * C, hp.actK[l], G, ncta);
+    *gC = plan_gemm(C, hp.PO, hp.PO4, hp.PO4, hp.actK[L - 1], G, ncta);
+  }
+  *use_tc = tc ? 1 : 0;
+}
+
 struct Workspace {
   long long off_ctr, off_err, off_prof, off_act[MAXL], off_cst, off_partA, off_partC, off_xw, total;
 };
@@ -877,16 +1079,18 @@ void layout_workspace(const ntm_b200_shape* s, const HostPlan& hp, long long B, 
   ws->off_prof = take(8ll * 16 * 1024);   // directly after ctr/err: zeroed by the same memset
   for (int l = 0; l < L; ++l) ws->off_act[l] = take(4ll * Gm * hp.actK[l]);
   ws->off_cst = take(4ll * Gm * L * C);
-  // partial-slab sizes: maximum over every resident-sequence count the launch may end up with
+  // partial-slab sizes: maximum over every resident-sequence count the launch may end up with,
+  // on either GEMM path
   long long pa = 0, pc = 0;
   for (int G = 1; G <= Gm; ++G) {
     const int ncta = G * hp.CS;
-    for (int l = 0; l < L; ++l) {
-      GemmPlan g = plan_gemm(hp.actK[l], 4 * C, 4 * C, 4 * C, hp.actK[l], G, ncta);
-      pa = std::max(pa, 4ll * g.KS * g.Gpad * g.NCs);
+    for (int variant = 0; variant < 2; ++variant) {
+      GemmPlan gA[MAXL], gC;
+      int use_tc = 0;
+      choose_plans(s, hp, G, ncta, variant == 1, gA, &gC, &use_tc);
+      for (int l = 0; l < L; ++l) pa = std::max(pa, 4ll * gA[l].KS * gA[l].Gpad * gA[l].NCs);
+      pc = std::max(pc, 4ll * gC.KS * gC.Gpad * gC.NCs);
     }
-    GemmPlan gc = plan_gemm(C, hp.PO, hp.PO4, hp.PO4, hp.actK[L - 1], G, ncta);
-    pc = std::max(pc, 4ll * gc.KS * gc.Gpad * gc.NCs);
   }
   ws->off_partA = take(pa);
   ws->off_partC = take(pc);
@@ -1073,11 +1277,12 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   for (int l = 0; l < L; ++l) {
     p.actK[l] = hp.actK[l];
     p.act[l] = reinterpret_cast<float*>(wsb + ws.off_act[l]);
-    p.gA[l] = plan_gemm(hp.actK[l], 4 * C, 4 * C, 4 * C, hp.actK[l], G, ncta);
     p.wA[l] = weights->lstm_w[l] + (l == 0 ? (size_t)shape->input_dim * 4 * C : 0);
     p.bA[l] = weights->lstm_b[l];
   }
-  p.gC = plan_gemm(C, hp.PO, hp.PO4, hp.PO4, hp.actK[L - 1], G, ncta);
+  choose_plans(shape, hp, G, ncta, true, p.gA, &p.gC, &p.use_tc);
+  g_last_info[0] = p.use_tc; g_last_info[1] = G; g_last_info[2] = ncta; g_last_info[3] = hp.CS;
+  g_last_info[4] = p.gA[0].KS; g_last_info[5] = p.gA[0].KW; g_last_info[6] = p.gC.KS; g_last_info[7] = p.gC.KW;
   p.wC = static_cast<const float*>(packed);
   p.bC = p.wC + (size_t)C * hp.PO4;
   p.xw = xw;
@@ -1096,7 +1301,7 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   p.prof = prof ? reinterpret_cast<long long*>(wsb + ws.off_prof) : nullptr;
   p.oMs = hp.oMs; p.oW0 = hp.oW0; p.oW1 = hp.oW1; p.oCn = hp.oCn; p.oX0 = hp.oX0; p.oX1 = hp.oX1;
   p.oScr = hp.oScr; p.oSim = hp.oSim; p.oWg = hp.oWg; p.oK = hp.oK; p.oE = hp.oE; p.oA = hp.oA;
-  p.oSm = hp.oSm; p.oLog = hp.oLog;
+  p.oSm = hp.oSm; p.oLog = hp.oLog; p.oTc = hp.oTc;
 
   e = cudaMemsetAsync(wsb + ws.off_ctr, 0, 512 + 8 * 16 * 1024, stream);   // barrier counter, error flag, phase counters
   if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync");
@@ -1128,6 +1333,12 @@ int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weigh
                       int64_t workspace_bytes, void* stream) {
   return ntm_b200_forward_seq(shape, weights, packed, batch, 1, inputs, state_in, state_out, logits,
                               outputs, debug_taps, workspace, workspace_bytes, stream);
+}
+
+int32_t ntm_b200_last_launch_info(int32_t* out8) {
+  if (!out8) return NTM_B200_ERR_NULL_POINTER;
+  for (int i = 0; i < 8; ++i) out8[i] = g_last_info[i];
+  return NTM_B200_OK;
 }
 
 int32_t ntm_b200_set_profiling(int32_t enable) {

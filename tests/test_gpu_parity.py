@@ -16,6 +16,19 @@ from oracle import ntm_oracle as O  # noqa: E402
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
+
+@pytest.fixture(autouse=True, params=["tensor", "simt"])
+def gemm_path(request):
+    """Every parity test runs on both controller-GEMM paths: the tcgen05 path (weights
+    resident in TMEM; the library still picks SIMT where the tiles do not fit) and the
+    forced fp32 SIMT path."""
+    if request.param == "simt":
+        os.environ["NTM_B200_DISABLE_TC"] = "1"
+    else:
+        os.environ.pop("NTM_B200_DISABLE_TC", None)
+    yield request.param
+    os.environ.pop("NTM_B200_DISABLE_TC", None)
+
 CASES = ["small_r2w1_l2", "small_writefirst_s2", "c1_copy", "c2_tracker_b2t4", "defaults_r3w3_l3"]
 
 
@@ -129,10 +142,14 @@ def test_c1_copy_full_config():
     assert max(errs.values()) <= TOL, errs
 
 
-def test_c2_tracker_full_config():
+def test_c2_tracker_full_config(gemm_path):
     """BASELINE config 2 exactly: N128 M512 4R+1W LSTM200 B64 T32 (2-CTA clusters)."""
+    from ntm_tracker_b200 import _cabi
     kw, B, T = O.CONFIGS["c2_tracker"]
     errs, _, _ = run_vs_oracle(O.NTMShape(**kw), B, T, 22)
+    info = _cabi.last_launch_info()
+    assert info["tensor_path"] == (1 if gemm_path == "tensor" else 0), info
+    assert info["cluster_size"] == 2 and info["sequences_resident"] == 64
     assert max(errs.values()) <= TOL, errs
 
 
