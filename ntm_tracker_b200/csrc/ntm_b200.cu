@@ -113,6 +113,42 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// v + sum over K-slices ks (ascending: fixed summation order) of p[ks * stride], with the loads of
+// each group of four issued before any of them is consumed (L2 latency overlapped).
+__device__ __forceinline__ float sum_slabs(const float* p, size_t stride, int KS, float v) {
+  int ks = 0;
+  for (; ks + 4 <= KS; ks += 4) {
+    const float a = __ldcg(p + (size_t)ks * stride), b = __ldcg(p + (size_t)(ks + 1) * stride);
+    const float c = __ldcg(p + (size_t)(ks + 2) * stride), d = __ldcg(p + (size_t)(ks + 3) * stride);
+    v += a; v += b; v += c; v += d;
+  }
+  if (ks < KS) {
+    const float a = __ldcg(p + (size_t)ks * stride);
+    const float b = (ks + 1 < KS) ? __ldcg(p + (size_t)(ks + 1) * stride) : 0.0f;
+    const float c = (ks + 2 < KS) ? __ldcg(p + (size_t)(ks + 2) * stride) : 0.0f;
+    v += a;
+    if (ks + 1 < KS) v += b;
+    if (ks + 2 < KS) v += c;
+  }
+  return v;
+}
+__device__ __forceinline__ float4 sum_slabs4(const float4* p, size_t stride4, int KS, float4 v) {
+  int ks = 0;
+  for (; ks + 4 <= KS; ks += 4) {
+    const float4 a = __ldcg(p + (size_t)ks * stride4), b = __ldcg(p + (size_t)(ks + 1) * stride4);
+    const float4 c = __ldcg(p + (size_t)(ks + 2) * stride4), d = __ldcg(p + (size_t)(ks + 3) * stride4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+  }
+  for (; ks < KS; ++ks) {
+    const float4 a = __ldcg(p + (size_t)ks * stride4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  return v;
+}
+
 // Phase-cycle accounting for the bench harness (thread 0 of each CTA; null = off).
 __device__ __forceinline__ void mark_slot(long long* row, long long& tmark, int slot) {
   if (row != nullptr && threadIdx.x == 0) {
@@ -370,10 +406,7 @@ __device__ __forceinline__ void lstm_phase(const KParams& p, int l, int Gcur, in
     const int col = q * C + u;
     float v = (l == 0) ? __ldg(p.xw + ((size_t)(b0 + b) * p.T + t) * (size_t)(4 * C) + col)
                        : __ldg(p.bA[l] + col);
-    const float* pa = p.partA + (size_t)b * g.NCs + col;
-    const size_t slab = (size_t)g.Gpad * g.NCs;
-#pragma unroll 8
-    for (int ks = 0; ks < KS; ++ks) v += __ldcg(pa + (size_t)ks * slab);
+    v = sum_slabs(p.partA + (size_t)b * g.NCs + col, (size_t)g.Gpad * g.NCs, KS, v);
     const unsigned lane = threadIdx.x & 31u, gl = lane & ~3u;
     const float zi = __shfl_sync(0xffffffffu, v, gl + 0);
     const float zj = __shfl_sync(0xffffffffu, v, gl + 1);
@@ -438,100 +471,92 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   float* eS = smem + p.oE;                       // [W][M4]
   float* aS = smem + p.oA;                       // [W][M4]
   float* sm = smem + p.oSm;                      // beta[H] g[H] gamma[H] rs[H] sw[H][SMAX]
-  float* sBeta = sm, *sG = sm + H, *sGam = sm + 2 * H, *sRs = sm + 3 * H, *sSw = sm + 4 * H;
-  float* sLog = smem + p.oLog;                   // [O]
+  float* sBeta = sm, *sG = sm + H, *sGam = sm + 2 * H, *sSw = sm + 4 * H;
+  float* sPart = sm + 4 * H + H * SMAX;          // [NWARP][H] per-warp partial key norms
   const bool last = (t == p.T - 1);
   float* dbg = (p.dbg != nullptr && last && crank == 0) ? p.dbg + (size_t)bglob * p.dbgStride : nullptr;
 
   // ---- D0: split-K reduction of phase C + bias, activations (ntm_cell.py:124-196) ----
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
             offE = offGam + H, offA = offE + M * W;
-  for (int i = tid; i < (H + 2 * W) * M4; i += NT) kS[i] = 0.0f;   // kS,eS,aS contiguous: zero pad lanes
-  __syncthreads();
-  for (int q = tid; q < p.PO; q += NT) {
-    float v = __ldg(p.bC + q);
-    {
-      const float* pc = p.partC + (size_t)gslot * p.gC.NCs + q;
-      const size_t slab = (size_t)p.gC.Gpad * p.gC.NCs;
-      const int KSc = p.gC.KS;
-#pragma unroll 8
-      for (int ks = 0; ks < KSc; ++ks) v += __ldcg(pc + (size_t)ks * slab);
-    }
-    if (q < offBeta) {
-      const int h = q / M, d = q - h * M;
-      const float kv = tanhf(v);
-      kS[h * M4 + d] = kv;
-      if (dbg) dbg[q] = kv;
-    } else if (q < offG) {
-      const float bv = softplus_f(v);
-      sBeta[q - offBeta] = bv;
-      if (dbg) dbg[q] = bv;
-    } else if (q < offS) {
-      const float gv = sigmoid_f(v);
-      sG[q - offG] = gv;
-      if (dbg) dbg[q] = gv;
-    } else if (q < offGam) {
-      const int idx = q - offS, h = idx / S, s = idx - h * S;
-      sSw[h * SMAX + s] = v;   // softmax over S below
-    } else if (q < offE) {
-      const float gv = 1.0f + softplus_f(v);
-      sGam[q - offGam] = gv;
-      if (dbg) dbg[q] = gv;
-    } else if (q < offA) {
-      const int idx = q - offE, h = idx / M, d = idx - h * M;
-      const float ev = sigmoid_f(v);
-      eS[h * M4 + d] = ev;
-      if (dbg) dbg[q] = ev;
-    } else if (q < p.P) {
-      const int idx = q - offA, h = idx / M, d = idx - h * M;
-      const float av = tanhf(v);
-      aS[h * M4 + d] = av;
-      if (dbg) dbg[q] = av;
-    } else {
-      sLog[q - p.P] = v;
-    }
+  // pass a: raw[q] = bias[q] + sum_ks partC[ks][slot][q], float4-vectorised.  `raw` lives in the
+  // wg scratch (never written by a peer CTA; simA is, by the pass-1 all-gather).
+  float* raw = wg;
+  {
+    const float4* pc4 = reinterpret_cast<const float4*>(p.partC + (size_t)gslot * p.gC.NCs);
+    const float4* b4 = reinterpret_cast<const float4*>(p.bC);
+    const size_t slab4 = (size_t)p.gC.Gpad * p.gC.NCs / 4;
+    for (int q4 = tid; q4 < p.PO4 / 4; q4 += NT)
+      reinterpret_cast<float4*>(raw)[q4] = sum_slabs4(pc4 + q4, slab4, p.gC.KS, __ldg(b4 + q4));
   }
   __syncthreads();
-  // key norms (ops.py:152), shift softmax (ntm_cell.py:161), output softmax (:220-221)
-  for (int h = warp; h < H; h += NWARP) {
-    float s = 0.0f;
-    for (int d = lane; d < M; d += 32) {
-      const float v = kS[h * M4 + d];
-      s = fmaf(v, v, s);
+  // pass b: activations.  Keys: kS[h][d] = tanh(raw) * cn[d]  (the key's own 1/|k| is a per-head
+  // scalar and is applied to the similarities later); per-head sum of squares via fixed-order
+  // warp partials.  Pad lanes d >= M are written as zeros.
+  {
+    float ss[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      ss[h] = 0.0f;
+      for (int d = tid; d < M4; d += NT) {
+        float kv = 0.0f;
+        if (d < M) {
+          kv = tanhf(raw[h * M + d]);
+          if (dbg) dbg[h * M + d] = kv;
+        }
+        kS[h * M4 + d] = kv * cn[d];
+        ss[h] = fmaf(kv, kv, ss[h]);
+      }
+      ss[h] = warp_sum(ss[h]);
     }
-    s = warp_sum(s);
-    if (lane == 0) sRs[h] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
+    }
+#pragma unroll
+    for (int h = 0; h < W; ++h) {
+      for (int d = tid; d < M4; d += NT) {
+        float ev = 0.0f, av = 0.0f;
+        if (d < M) {
+          ev = sigmoid_f(raw[offE + h * M + d]);
+          av = tanhf(raw[offA + h * M + d]);
+          if (dbg) { dbg[offE + h * M + d] = ev; dbg[offA + h * M + d] = av; }
+        }
+        eS[h * M4 + d] = ev;
+        aS[h * M4 + d] = av;
+      }
+    }
   }
-  if (tid < H) {
-    float* s = sSw + tid * SMAX;
-    float mx = s[0];
-    for (int i = 1; i < S; ++i) mx = fmaxf(mx, s[i]);
+  if (tid < H) {   // per-head scalars: beta, g, gamma (ntm_cell.py:140,151,169), shift softmax (:161)
+    const float bv = softplus_f(raw[offBeta + tid]);
+    const float gv = sigmoid_f(raw[offG + tid]);
+    const float gm = 1.0f + softplus_f(raw[offGam + tid]);
+    sBeta[tid] = bv; sG[tid] = gv; sGam[tid] = gm;
+    float* sp = sSw + tid * SMAX;
+    float mx = raw[offS + tid * S];
+    for (int i = 1; i < S; ++i) mx = fmaxf(mx, raw[offS + tid * S + i]);
     float sum = 0.0f;
-    for (int i = 0; i < S; ++i) { s[i] = expf(s[i] - mx); sum += s[i]; }
-    for (int i = 0; i < S; ++i) {
-      s[i] = s[i] / sum;
-      if (dbg) dbg[offS + tid * S + i] = s[i];
+    for (int i = 0; i < S; ++i) { sp[i] = expf(raw[offS + tid * S + i] - mx); sum += sp[i]; }
+    for (int i = 0; i < S; ++i) sp[i] = sp[i] / sum;
+    if (dbg) {
+      dbg[offBeta + tid] = bv; dbg[offG + tid] = gv; dbg[offGam + tid] = gm;
+      for (int i = 0; i < S; ++i) dbg[offS + tid * S + i] = sp[i];
     }
   }
-  if (crank == 0 && tid == NT - 1) {
+  if (crank == 0 && tid == NT - 1) {   // output projection + softmax (ntm_cell.py:220-221)
     const size_t o = ((size_t)bglob * p.T + t) * p.O;
-    float mx = sLog[0];
-    for (int i = 1; i < p.O; ++i) mx = fmaxf(mx, sLog[i]);
+    const float* lg = raw + p.P;
+    float mx = lg[0];
+    for (int i = 1; i < p.O; ++i) mx = fmaxf(mx, lg[i]);
     float sum = 0.0f;
-    for (int i = 0; i < p.O; ++i) sum += expf(sLog[i] - mx);
+    for (int i = 0; i < p.O; ++i) sum += expf(lg[i] - mx);
     for (int i = 0; i < p.O; ++i) {
-      p.logits[o + i] = sLog[i];
-      if (p.outputs) p.outputs[o + i] = expf(sLog[i] - mx) / sum;
+      p.logits[o + i] = lg[i];
+      if (p.outputs) p.outputs[o + i] = expf(lg[i] - mx) / sum;
     }
   }
   __syncthreads();
   mark_slot(prow, tmark, 10);
-  // kc[h][d] = k[h][d] * rs[h] * cn[d]   (in place)
-  for (int i = tid; i < H * M4; i += NT) {
-    const int h = i / M4, d = i - h * M4;
-    kS[i] = kS[i] * sRs[h] * cn[d];
-  }
-  __syncthreads();
 
   // ---- pass 1: sim[h][n] = sum_d kc[h][d] * M[n][d] over this CTA's rows (ops.py:156) ----
   {
@@ -598,22 +623,30 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   for (int h = warp; h < H; h += NWARP) {
     float* sh = simA + h * Npad;
     float* gh = wg + h * Npad;
-    const float beta = sBeta[h], gate = sG[h], gamma = sGam[h];
+    const float gate = sG[h], gamma = sGam[h];
+    float kn = 0.0f;                                  // |k_h|^2, fixed summation order
+    for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+    const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));   // ops.py:152
+    const float beta = sBeta[h];
     float mx = -INFINITY;
+#pragma unroll 4
     for (int n = lane; n < N; n += 32) {
-      const float x = sh[n] * beta;
-      if (dbg) dbg[p.P + (0 * H + h) * N + n] = sh[n];
+      const float sv = sh[n] * rs;                    // similarity (ops.py:156)
+      const float x = sv * beta;
+      if (dbg) dbg[p.P + (0 * H + h) * N + n] = sv;
       sh[n] = x;
       mx = fmaxf(mx, x);
     }
     mx = warp_max(mx);
     float sum = 0.0f;
+#pragma unroll 4
     for (int n = lane; n < N; n += 32) {
       const float e = expf(sh[n] - mx);
       sh[n] = e;
       sum += e;
     }
     sum = warp_sum(sum);
+#pragma unroll 4
     for (int n = lane; n < N; n += 32) {
       const float wc = sh[n] / sum;
       const float v = wc * gate + wprev[h * Npad + n] * (1.0f - gate);
@@ -625,6 +658,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
     __syncwarp();
     float psum = 0.0f;
+#pragma unroll 4
     for (int n = lane; n < N; n += 32) {
       float conv = 0.0f;
       for (int s = 0; s < S; ++s) {
@@ -642,6 +676,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
     psum = warp_sum(psum);
     const float den = psum + 1e-3f;          // ntm_cell.py:175-176
+#pragma unroll 4
     for (int n = lane; n < N; n += 32) {
       const float wv = sh[n] / den;
       wnew[h * Npad + n] = wv;
@@ -774,7 +809,11 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
     ntm_b200::umma::tcgen05_fence_after();
   }
   long long tmark = clock64();
-  long long* prow = p.prof ? p.prof + (size_t)cta * 16 : nullptr;
+  // phase-cycle accumulators live in shared memory (a global read-modify-write per mark would sit
+  // on the critical path); flushed to p.prof once at the end
+  long long* prow = p.prof ? reinterpret_cast<long long*>(smem + p.oTc + 4) : nullptr;
+  if (prow != nullptr && tid < 16) prow[tid] = 0;
+  __syncthreads();
   auto mark = [&](int slot) { mark_slot(prow, tmark, slot); };
 
   for (int b0 = 0; b0 < p.B; b0 += p.G) {
@@ -860,6 +899,10 @@ __global__ void __launch_bounds__(NT, 1) ntm_seq_kernel(const KParams p) {
     }
     cluster.sync();   // no CTA re-enters the prologue while a peer still reads its shared memory
     mark(9);
+  }
+  if (prow != nullptr) {
+    __syncthreads();
+    if (tid < 16) p.prof[(size_t)cta * 16 + tid] = prow[tid];
   }
   if (p.use_tc) {
     ntm_b200::umma::tcgen05_fence_before();
@@ -953,17 +996,18 @@ long long layout_for(const ntm_b200_shape* s, int CS, HostPlan* hp) {
   hp->oCn = take(hp->M4);
   hp->oX0 = take((R + 1) * hp->M4);
   hp->oX1 = take((R + 1) * hp->M4);
-  hp->oTc = take(4);
+  hp->oTc = take(4 + 32);   // mbarrier + TMEM base, then 16 int64 phase-cycle accumulators
   hp->oScr = o;
   // phase-D temporaries inside the scratch union
   int d = o;
   auto taked = [&](int n) { int r = d; d += round_up(n, 4); return r; };
-  hp->oSim = taked(H * hp->Npad);
-  hp->oWg = taked(H * hp->Npad);
+  // [sim | wg] are contiguous and together also hold the raw head-parameter vector (PO4 floats)
+  hp->oSim = taked(H * hp->Npad);                      // written by peer CTAs (all-gather)
+  hp->oWg = taked(std::max(H * hp->Npad, hp->PO4));    // also holds the raw head-parameter vector
   hp->oK = taked(H * hp->M4);      // kS, eS, aS must stay contiguous (zero-filled together)
   hp->oE = taked(W * hp->M4);
   hp->oA = taked(W * hp->M4);
-  hp->oSm = taked(4 * H + H * SMAX);
+  hp->oSm = taked(4 * H + H * SMAX + NWARP * H);
   hp->oLog = taked(s->output_dim);
   const int dfl = d - o;
   hp->scr_floats = std::max(dfl, STAGE_BUDGET_BYTES / 4);
