@@ -212,6 +212,7 @@ def main():
     import __graft_entry__ as entry
     entry.build()
     from ntm_tracker_b200 import LoopNTMTracker, _cabi
+    from ntm_tracker_b200.sharding import max_over_ranks, shard_range
     from oracle import ntm_oracle as O    # shapes / config table only (no oracle compute here)
     import ctypes as C
 
@@ -230,8 +231,7 @@ def main():
         T = args.seq_len
     if scaling == "strong":
         B_total = B
-        lo = rank * B // world
-        hi = (rank + 1) * B // world
+        lo, hi = shard_range(B, world, rank)
         B_local = hi - lo
     else:
         B_local = B
@@ -295,10 +295,7 @@ def main():
     launches = lib.ntm_b200_launch_count() - launches0
     trk.cell.finish()
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = max_over_ranks(sum(step_ms), dev)
     value = B_total * T * args.steps / (total_ms / 1e3)
 
     # ---------------- end-to-end: pinned host inputs in, host results out ------------------
@@ -311,10 +308,8 @@ def main():
         for i in range(args.steps):
             out_h, log_h = trk(x_host, state)     # H2D copy, kernels, D2H of outputs + logits
         barrier()
-        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e = {"value": B_total * T * args.steps / float(e2e_s.item()), "unit": "seq-steps/s",
+        e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+        e2e = {"value": B_total * T * args.steps / e2e_s, "unit": "seq-steps/s",
                "h2d_bytes_per_step": int(input_bytes) * world,
                "d2h_bytes_per_step": int(out_h.numel() + log_h.numel()) * 4 * world}
     clocks = sampler.stop() if rank == 0 else None

@@ -490,6 +490,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
       reinterpret_cast<float4*>(raw)[q4] = sum_slabs4(pc4 + q4, slab4, p.gC.KS, __ldg(b4 + q4));
   }
   __syncthreads();
+  mark_slot(prow, tmark, 15);
   // pass b: activations.  Keys: kS[h][d] = tanh(raw) * cn[d]  (the key's own 1/|k| is a per-head
   // scalar and is applied to the similarities later); per-head sum of squares via fixed-order
   // warp partials.  Pad lanes d >= M are written as zeros.
@@ -1352,7 +1353,10 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
 
   if (prof) cudaEventRecord(g_ev[1], stream);
   cfg.gridDim = dim3(ncta);
-  cfg.numAttrs = 2;   // cluster + cooperative (co-residency enforced by the driver)
+  // cluster + cooperative (co-residency enforced by the driver).  NTM_B200_NO_COOP=1 drops the
+  // cooperative attribute (the grid is sized from the occupancy query, so the CTAs are still
+  // co-resident); needed under Nsight Compute, whose kernel replay rejects cooperative+cluster launches.
+  cfg.numAttrs = getenv("NTM_B200_NO_COOP") ? 1 : 2;
   e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) {
     // some driver/toolkit combinations reject cooperative+cluster; the grid is

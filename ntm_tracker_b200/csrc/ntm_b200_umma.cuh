@@ -121,11 +121,12 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k, int nr
 
 // fp32 pair -> packed bf16 "hi" word and "lo" (residual) word; low half = lower k.
 __device__ __forceinline__ void split_pack_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-  const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  // one packed cvt.rn.bf16x2.f32 per pair (the scalar F2F conversions run on a slow pipe)
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ---- MMA issue (one elected thread) ----

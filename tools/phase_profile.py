@@ -47,7 +47,7 @@ waves = -(-B // plan["sequences_resident"])
 steps = waves * T
 names = ["A gemm", "A barrier", "B lstm", "B barrier", "C gemm", "C barrier", "D addressing",
          "D barrier", "prologue", "epilogue", "D.0 params+acts", "D.1 kc+pass1+csync",
-         "D.2 addressing", "D.3 pass2+csync", "D.4 finalize", "-"]
+         "D.2 addressing", "D.3 pass2+csync", "D.4 finalize", "D.0a param loads"]
 mhz = 1965.0
 res = {"workload": wl, "B": B, "T": T, "ncta": ncta, "waves": waves, "seq_kernel_ms": b.value,
        "xproj_ms": a.value, "us_per_step": b.value * 1e3 / steps, "phases_us_per_step": {}}
