@@ -157,10 +157,32 @@ def cpu_reference_run(cfg_name, steps, warmup, threads=None):
     return Bs * Ts / med, cores, sample, med * 1e3
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr, so that
+    stdout carries exactly one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference_impl(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    protect_stdout()
     cfg_name, scaling = WORKLOADS[args.workload]
     from oracle import ntm_oracle as O
     kw, B, T = O.CONFIGS[cfg_name]
@@ -177,7 +199,7 @@ def run_reference_impl(args):
         "note": "reference is TF1/Python-2 graph code (not installable here); this is the fp32 "
                 "op-for-op torch-CPU restatement oracle/ntm_ref_torch.py on the host cores",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -206,6 +228,7 @@ def main():
         return subprocess.call(cmd)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    protect_stdout()
 
     import torch
     import torch.distributed as dist
@@ -367,7 +390,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu,
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -89,6 +89,8 @@ typedef struct ntm_b200_plan {
   int32_t rows_per_cta;        /* memory rows resident in each CTA's shared memory */
   int32_t sequences_resident;  /* sequences advanced concurrently per wave */
   int32_t threads_per_cta;
+  int32_t ctas_per_sm;         /* co-resident CTAs per SM the chosen kernel shape is built for */
+  int32_t teams;               /* decoupled groups of CTAs, each advancing its own sequences */
   int64_t smem_bytes_per_cta;
   int64_t workspace_bytes;     /* for ntm_b200_forward_seq with this (B, T) */
   int64_t packed_bytes;        /* for ntm_b200_pack_weights */
@@ -157,10 +159,11 @@ int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms);
  * (synchronous; call after the stream has been synchronised). */
 int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_ctas);
 
-/* Geometry of this thread's last ntm_b200_forward_seq launch: {tensor path used (0/1),
+/* Geometry of this thread's last ntm_b200_forward_seq launch, 16 ints: {tensor path used (0/1),
  * resident sequences, CTAs, cluster size, K-slices and K-slice width of the layer-0 controller
- * GEMM, K-slices and K-slice width of the head-parameter GEMM}. */
-int32_t ntm_b200_last_launch_info(int32_t* out8);
+ * GEMM, K-slices and K-slice width of the head-parameter GEMM, teams, threads per CTA, CTAs per
+ * SM, shared-memory bytes per CTA, 0...}. */
+int32_t ntm_b200_last_launch_info(int32_t* out16);
 
 /* Number of kernel launches the library has issued in this process (for the
  * bench harness' `gpu_launches` claim). */

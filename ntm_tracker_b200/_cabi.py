@@ -39,6 +39,7 @@ class State(C.Structure):
 class Plan(C.Structure):
     _fields_ = [("cluster_size", C.c_int32), ("rows_per_cta", C.c_int32),
                 ("sequences_resident", C.c_int32), ("threads_per_cta", C.c_int32),
+                ("ctas_per_sm", C.c_int32), ("teams", C.c_int32),
                 ("smem_bytes_per_cta", C.c_int64), ("workspace_bytes", C.c_int64),
                 ("packed_bytes", C.c_int64), ("debug_floats_per_sequence", C.c_int64)]
 
@@ -102,7 +103,8 @@ def check(status, what):
 
 def last_launch_info():
     """{'tensor_path', 'sequences_resident', 'ctas', 'cluster_size', ...} of this thread's last launch."""
-    buf = (C.c_int32 * 8)()
+    buf = (C.c_int32 * 16)()
     check(load().ntm_b200_last_launch_info(buf), "last_launch_info")
-    keys = ("tensor_path", "sequences_resident", "ctas", "cluster_size", "ks_ctrl", "kw_ctrl", "ks_heads", "kw_heads")
+    keys = ("tensor_path", "sequences_resident", "ctas", "cluster_size", "ks_ctrl", "kw_ctrl", "ks_heads",
+            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta")
     return dict(zip(keys, list(buf)))

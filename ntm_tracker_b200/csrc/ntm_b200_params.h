@@ -1,0 +1,81 @@
+// ntm_b200_params.h -- launch parameters shared by the host side (ntm_b200.cu) and the two
+// compilations of the persistent kernel (512 threads x 1 CTA/SM, 256 threads x 2 CTAs/SM).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ntm_b200.h"
+
+namespace ntm_b200 {
+
+constexpr int RB = 4;            // memory rows per warp-group in pass 1
+constexpr int TBMAX = 16;        // max sequences per warp tile in the SIMT skinny GEMMs
+constexpr int MAXL = NTM_B200_MAX_LAYERS;
+constexpr int SMAX = 2 * NTM_B200_MAX_SHIFT_RANGE + 1;
+constexpr int B200_SMS = 148;
+constexpr int B200_SMEM_OPTIN = 232448;   // 227 KiB per CTA
+constexpr int B200_SMEM_SM = 233472;      // 228 KiB per SM (1 KiB reserved per resident CTA)
+constexpr int PROF_SLOTS = 16;
+
+struct GemmPlan {
+  int K, NC, NCs, ldw, lda;            // NCs: row stride of the partial slabs
+  int KS, KW, JW, NBT, TB, Gpad, njg, units;
+  int tc;      // 1: tcgen05 path (128-column weight tiles resident in TMEM), 0: SIMT path
+  int tcol;    // tc: first TMEM column of this GEMM's weight tile (KW/2 "hi" columns, then KW/2 "lo")
+};
+
+// One launch = `nteams` decoupled teams of `team_ctas` CTAs.  A team owns its own resident
+// sequences, workspace slices and barrier counter and runs the four-phase timestep loop on its
+// own; with two teams co-resident on every SM one team's barrier / latency bubbles are filled by
+// the other's work.
+struct KParams {
+  int D, O, N, M, M4, MC, S, C, L, H, P, PO, PO4, write_first, shift0;
+  int B, T, CS, NR, G, Npad;           // G: resident sequences (clusters) PER TEAM
+  int nteams, team_ctas, tmem_cols;
+  GemmPlan gA[MAXL];
+  GemmPlan gC;
+  const float* wA[MAXL];
+  const float* bA[MAXL];
+  const float* wC;
+  const float* bC;
+  const float* xw;
+  const float *sM, *sw, *sread, *sctrl;
+  long long ssM, ssw, ssread, ssctrl;
+  float *dM, *dw, *dread, *dctrl;
+  long long dsM, dsw, dsread, dsctrl;
+  float* logits;
+  float* outputs;
+  float* dbg;
+  long long dbgStride;
+  float* act[MAXL];                    // team 0's slice; team t at + t * act_ts[l]
+  long long act_ts[MAXL];
+  int actK[MAXL];
+  float* cst;
+  long long cst_ts;
+  float* partA;
+  long long partA_ts;
+  float* partC;
+  long long partC_ts;
+  unsigned* ctr;                       // team t's barrier counter at ctr + 32 * t (128 B apart)
+  int* err;
+  long long* prof;                     // [grid CTAs][PROF_SLOTS] phase-cycle counters, or null
+  // shared-memory carve-up, offsets in floats
+  int oMs, oW0, oW1, oCn, oScr;
+  int oSim, oWg, oK, oE, oA, oSm;
+  int oTc;       // 4 floats: mbarrier (8 B) + TMEM base address (4 B); then 32 floats of phase counters
+  int use_tc;    // any GEMM on the tensor path -> allocate TMEM
+};
+
+// Entry points each kernel compilation exports (namespaces k512 / k256).
+struct KernelVariant {
+  int threads;          // CTA size
+  int ctas_per_sm;      // co-resident CTAs per SM the variant is built for
+  bool cooperative_ok;  // the driver accepts a cooperative launch of a full grid of this build
+  cudaError_t (*set_smem)(int R, int W, int smem_bytes);
+  cudaError_t (*max_clusters)(int R, int W, int cluster_size, int grid_ctas, int smem_bytes, int* out);
+  cudaError_t (*launch)(int R, int W, const KParams& p, int grid_ctas, int cluster_size, int smem_bytes,
+                        bool cooperative, cudaStream_t stream);
+};
+namespace k512 { const KernelVariant& variant(); }
+namespace k256 { const KernelVariant& variant(); }
+
+}  // namespace ntm_b200

@@ -58,6 +58,7 @@ def test_plan_tracker_config_uses_cta_pairs(lib):
     st, plan = query(lib, shape(), 64, 32)
     assert st == 0
     assert plan.cluster_size == 2 and plan.rows_per_cta == 64
+    assert plan.threads_per_cta == 512 and plan.ctas_per_sm == 1 and plan.teams == 1
     assert plan.sequences_resident == 64
     assert plan.smem_bytes_per_cta <= 232448
     st, plan = query(lib, shape(), 4096, 64)
@@ -68,6 +69,7 @@ def test_plan_tracker_config_uses_cta_pairs(lib):
 def test_plan_large_memory_uses_8_cta_clusters(lib):
     st, plan = query(lib, shape(mem_size=1024, mem_dim=256), 512, 128)
     assert st == 0 and plan.cluster_size == 8 and plan.rows_per_cta == 128
+    assert plan.threads_per_cta == 512 and plan.ctas_per_sm == 1 and plan.teams == 1
     assert plan.smem_bytes_per_cta <= 232448
 
 

@@ -149,7 +149,7 @@ def test_c2_tracker_full_config(gemm_path):
     errs, _, _ = run_vs_oracle(O.NTMShape(**kw), B, T, 22)
     info = _cabi.last_launch_info()
     assert info["tensor_path"] == (1 if gemm_path == "tensor" else 0), info
-    assert info["cluster_size"] == 2 and info["sequences_resident"] == 64
+    assert info["sequences_resident"] == 64 and info["teams"] == 1 and info["cluster_size"] == 2
     assert max(errs.values()) <= TOL, errs
 
 

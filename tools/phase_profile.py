@@ -37,19 +37,20 @@ for _ in range(3):
     trk(x, state)
 trk.cell.finish()
 plan = trk.cell.plan(B, T)
-ncta = plan["sequences_resident"] * plan["cluster_size"]
+info = _cabi.last_launch_info()
+ncta = info["ctas"]
 buf = (C.c_int64 * (16 * ncta))()
 lib.ntm_b200_phase_cycles(trk.cell._last_ws.data_ptr(), buf, ncta)
 a, b = C.c_float(), C.c_float()
 lib.ntm_b200_last_kernel_ms(C.byref(a), C.byref(b))
 cyc = np.array(buf, dtype=np.int64).reshape(ncta, 16)
-waves = -(-B // plan["sequences_resident"])
+waves = -(-B // info["sequences_resident"])
 steps = waves * T
 names = ["A gemm", "A barrier", "B lstm", "B barrier", "C gemm", "C barrier", "D addressing",
          "D barrier", "prologue", "epilogue", "D.0 params+acts", "D.1 kc+pass1+csync",
          "D.2 addressing", "D.3 pass2+csync", "D.4 finalize", "D.0a param loads"]
 mhz = 1965.0
-res = {"workload": wl, "B": B, "T": T, "ncta": ncta, "waves": waves, "seq_kernel_ms": b.value,
+res = {"workload": wl, "B": B, "T": T, "ncta": ncta, "waves": waves, "launch": info, "seq_kernel_ms": b.value,
        "xproj_ms": a.value, "us_per_step": b.value * 1e3 / steps, "phases_us_per_step": {}}
 for i, n in enumerate(names):
     per = cyc[:, i] / mhz / (waves if i in (8, 9) else steps)
