@@ -89,7 +89,7 @@ struct HostPlan {
   int max_teams;        // 2 when two CTAs share an SM (two decoupled teams), else 1
   int Gteam_max;        // resident sequences per team (upper bound, before the occupancy query)
   int smem_floats;
-  int oMs, oW0, oW1, oCn, oScr, oSim, oWg, oK, oE, oA, oSm, oTc;
+  int oMs, oW0, oW1, oCn, oScr, oSim, oSl, oWg, oK, oE, oA, oSm, oTc;
   int scr_floats;
   int actK[MAXL];
   long long packed_bytes, debug_floats;
@@ -139,12 +139,13 @@ bool layout_for(const ntm_b200_shape* s, int CS, int nwarp, int budget, HostPlan
   // phase-D temporaries inside the scratch union
   int d = o;
   auto taked = [&](int n) { int r = d; d += round_up(n, 4); return r; };
-  hp->oSim = taked(H * hp->Npad);                      // written by peer CTAs (all-gather)
+  hp->oSim = taked(H * hp->Npad);                      // private full-length similarities
+  hp->oSl = taked(H * hp->NR);                         // this CTA's slice, pulled by the peers over DSMEM
   hp->oWg = taked(std::max(H * hp->Npad, hp->PO4));    // also holds the raw head-parameter vector
   hp->oK = taked(H * hp->M4);      // kS, eS, aS contiguous; kS doubles as the DSMEM exchange buffer
   hp->oE = taked(W * hp->M4);
   hp->oA = taked(W * hp->M4);
-  hp->oSm = taked(4 * H + H * SMAX + nwarp * H);
+  hp->oSm = taked(4 * H + H * SMAX + nwarp * H + 3 * nwarp);
   const int dfl = d - o;
   const int min_stage = 16 * 1024 / 4, max_stage = 44 * 1024 / 4;
   int scr = std::max(dfl, min_stage);
@@ -493,7 +494,7 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   p.err = reinterpret_cast<int*>(wsb + ws.off_err);
   p.prof = prof ? reinterpret_cast<long long*>(wsb + ws.off_prof) : nullptr;
   p.oMs = hp.oMs; p.oW0 = hp.oW0; p.oW1 = hp.oW1; p.oCn = hp.oCn;
-  p.oScr = hp.oScr; p.oSim = hp.oSim; p.oWg = hp.oWg; p.oK = hp.oK; p.oE = hp.oE; p.oA = hp.oA;
+  p.oScr = hp.oScr; p.oSim = hp.oSim; p.oSl = hp.oSl; p.oWg = hp.oWg; p.oK = hp.oK; p.oE = hp.oE; p.oA = hp.oA;
   p.oSm = hp.oSm; p.oTc = hp.oTc;
 
   e = cudaMemsetAsync(wsb + ws.off_ctr, 0, 512 + 8 * PROF_SLOTS * 1024, stream);   // barrier counter, error flag, phase counters

@@ -60,7 +60,7 @@ struct KParams {
   long long* prof;                     // [grid CTAs][PROF_SLOTS] phase-cycle counters, or null
   // shared-memory carve-up, offsets in floats
   int oMs, oW0, oW1, oCn, oScr;
-  int oSim, oWg, oK, oE, oA, oSm;
+  int oSim, oSl, oWg, oK, oE, oA, oSm;
   int oTc;       // 4 floats: mbarrier (8 B) + TMEM base address (4 B); then 32 floats of phase counters
   int use_tc;    // any GEMM on the tensor path -> allocate TMEM
 };

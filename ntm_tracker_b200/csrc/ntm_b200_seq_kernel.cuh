@@ -405,7 +405,8 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   // pass 1; (R+1) <= H rows).  Single-buffered: a peer only reads it in this step's finalize, and
   // three team-wide barriers separate that from the next overwrite.
   float* xch = smem + p.oK;
-  float* simA = smem + p.oSim;                   // [H][Npad]
+  float* simA = smem + p.oSim;                   // [H][Npad] private full-length similarities / weights
+  float* simL = smem + p.oSl;                    // [H][NR] this CTA's rows, read by the peers
   float* wg = smem + p.oWg;                      // [H][Npad]
   float* kS = smem + p.oK;                       // [H][M4]
   float* eS = smem + p.oE;                       // [W][M4]
@@ -413,6 +414,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   float* sm = smem + p.oSm;                      // beta[H] g[H] gamma[H] rs[H] sw[H][SMAX]
   float* sBeta = sm, *sG = sm + H, *sGam = sm + 2 * H, *sSw = sm + 4 * H;
   float* sPart = sm + 4 * H + H * SMAX;          // [NWARP][H] per-warp partial key norms
+  float* sRed = sPart + NWARP * H;               // [H][3][NWARP / H] addressing reductions
   const bool last = (t == p.T - 1);
   float* dbg = (p.dbg != nullptr && last && crank == 0) ? p.dbg + (size_t)bglob * p.dbgStride : nullptr;
 
@@ -547,81 +549,125 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
         for (int i = 0; i < RB; ++i) {
           const int rl = rb * RB + i;
           if (rl < nrows) {
-            for (int r = 0; r < p.CS; ++r) {
-              float* rem = cluster.map_shared_rank(simA, r);
 #pragma unroll
-              for (int h = 0; h < H; ++h) rem[h * Npad + row0 + rl] = acc[i][h];
-            }
+            for (int h = 0; h < H; ++h) simL[h * p.NR + rl] = acc[i][h];
           }
         }
       }
     }
   }
   cluster.sync();
+  // all-gather over DSMEM: every CTA pulls all slices (its own included) from the owners' simL
+  // buffers into its private full-length copy; simL is not touched again before the next step's
+  // pass 1, which three team-wide barriers separate from these reads.
+  for (int i = tid; i < H * N; i += NT) {
+    const int h = i / N, n = i - h * N;
+    const int q = n / p.NR;
+    const float* rem = cluster.map_shared_rank(simL, q);
+    simA[h * Npad + n] = rem[h * p.NR + (n - q * p.NR)];
+  }
+  __syncthreads();
   mark_slot(prow, tmark, 11);
 
   // ---- addressing on the full [H][N] weighting, replicated in every CTA (ntm_cell.py:140-176) ----
-  for (int h = warp; h < H; h += NWARP) {
-    float* sh = simA + h * Npad;
-    float* gh = wg + h * Npad;
-    const float gate = sG[h], gamma = sGam[h];
-    float kn = 0.0f;                                  // |k_h|^2, fixed summation order
-    for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
-    const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));   // ops.py:152
-    const float beta = sBeta[h];
-    float mx = -INFINITY;
-#pragma unroll 4
-    for (int n = lane; n < N; n += 32) {
-      const float sv = sh[n] * rs;                    // similarity (ops.py:156)
-      const float x = sv * beta;
-      if (dbg) dbg[p.P + (0 * H + h) * N + n] = sv;
-      sh[n] = x;
-      mx = fmaxf(mx, x);
-    }
-    mx = warp_max(mx);
-    float sum = 0.0f;
-#pragma unroll 4
-    for (int n = lane; n < N; n += 32) {
-      const float e = expf(sh[n] - mx);
-      sh[n] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-#pragma unroll 4
-    for (int n = lane; n < N; n += 32) {
-      const float wc = sh[n] / sum;
-      const float v = wc * gate + wprev[h * Npad + n] * (1.0f - gate);
-      gh[n] = v;
-      if (dbg) {
-        dbg[p.P + (1 * H + h) * N + n] = wc;
-        dbg[p.P + (2 * H + h) * N + n] = v;
+  // WPH warps cooperate on one head (elements strided over them); the three N-reductions go
+  // through shared memory in fixed (warp-ascending) order behind a named barrier per head.
+  {
+    constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
+    const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
+    const bool multi = (NWARP / H) > 0;                       // else: one warp walks the heads
+    const int hstep = multi ? H : NWARP;
+    for (int h = multi ? hgrp : warp; h < H; h += hstep) {
+      float* sh = simA + h * Npad;
+      float* gh = wg + h * Npad;
+      float* red = sRed + h * 3 * WPH;                        // [3][WPH] partial max / sum / psum
+      const int nstep = 32 * (multi ? WPH : 1);
+      const int n0 = 32 * (multi ? sub : 0) + lane;
+      const int nthr = 32 * WPH;
+      auto head_bar = [&]() {
+        if (multi && WPH > 1) asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(nthr) : "memory");
+        else __syncwarp();
+      };
+      const float gate = sG[h], gamma = sGam[h];
+      float kn = 0.0f;                                  // |k_h|^2, fixed summation order
+      for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+      const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));   // ops.py:152
+      const float beta = sBeta[h];
+      float mx = -INFINITY;
+#pragma unroll 2
+      for (int n = n0; n < N; n += nstep) {
+        const float sv = sh[n] * rs;                    // similarity (ops.py:156)
+        const float x = sv * beta;
+        if (dbg) dbg[p.P + (0 * H + h) * N + n] = sv;
+        sh[n] = x;
+        mx = fmaxf(mx, x);
       }
-    }
-    __syncwarp();
-    float psum = 0.0f;
-#pragma unroll 4
-    for (int n = lane; n < N; n += 32) {
-      float conv = 0.0f;
-      for (int s = 0; s < S; ++s) {
-        int idx = n + p.shift0 + s;          // circular_shift(x, j)[n] = x[(n + j) mod N], ops.py:216-242
-        idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
-        conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
+      mx = warp_max(mx);
+      if (multi && WPH > 1) {
+        if (lane == 0) red[sub] = mx;
+        head_bar();
+        mx = red[0];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) mx = fmaxf(mx, red[i]);
       }
-      const float pw = exp2f(gamma * log2f(conv));   // conv >= 0, gamma >= 1: == pow(conv, gamma), 0 -> 0
-      sh[n] = pw;
-      psum += pw;
-      if (dbg) {
-        dbg[p.P + (3 * H + h) * N + n] = conv;
-        dbg[p.P + (4 * H + h) * N + n] = pw;
+      float sum = 0.0f;
+#pragma unroll 2
+      for (int n = n0; n < N; n += nstep) {
+        const float e = expf(sh[n] - mx);
+        sh[n] = e;
+        sum += e;
       }
-    }
-    psum = warp_sum(psum);
-    const float den = psum + 1e-3f;          // ntm_cell.py:175-176
-#pragma unroll 4
-    for (int n = lane; n < N; n += 32) {
-      const float wv = sh[n] / den;
-      wnew[h * Npad + n] = wv;
-      if (last && crank == 0) p.dw[(size_t)bglob * p.dsw + h * N + n] = wv;
+      sum = warp_sum(sum);
+      if (multi && WPH > 1) {
+        if (lane == 0) red[WPH + sub] = sum;
+        head_bar();
+        sum = red[WPH];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) sum += red[WPH + i];
+      }
+#pragma unroll 2
+      for (int n = n0; n < N; n += nstep) {
+        const float wc = sh[n] / sum;
+        const float v = wc * gate + wprev[h * Npad + n] * (1.0f - gate);
+        gh[n] = v;
+        if (dbg) {
+          dbg[p.P + (1 * H + h) * N + n] = wc;
+          dbg[p.P + (2 * H + h) * N + n] = v;
+        }
+      }
+      head_bar();                                       // the shift reads neighbours' gated weights
+      float psum = 0.0f;
+#pragma unroll 2
+      for (int n = n0; n < N; n += nstep) {
+        float conv = 0.0f;
+        for (int s = 0; s < S; ++s) {
+          int idx = n + p.shift0 + s;          // circular_shift(x, j)[n] = x[(n + j) mod N], ops.py:216-242
+          idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+          conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
+        }
+        const float pw = exp2f(gamma * log2f(conv));   // conv >= 0, gamma >= 1: == pow(conv, gamma), 0 -> 0
+        sh[n] = pw;
+        psum += pw;
+        if (dbg) {
+          dbg[p.P + (3 * H + h) * N + n] = conv;
+          dbg[p.P + (4 * H + h) * N + n] = pw;
+        }
+      }
+      psum = warp_sum(psum);
+      if (multi && WPH > 1) {
+        if (lane == 0) red[2 * WPH + sub] = psum;
+        head_bar();
+        psum = red[2 * WPH];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) psum += red[2 * WPH + i];
+      }
+      const float den = psum + 1e-3f;          // ntm_cell.py:175-176
+#pragma unroll 2
+      for (int n = n0; n < N; n += nstep) {
+        const float wv = sh[n] / den;
+        wnew[h * Npad + n] = wv;
+        if (last && crank == 0) p.dw[(size_t)bglob * p.dsw + h * N + n] = wv;
+      }
     }
   }
   __syncthreads();
