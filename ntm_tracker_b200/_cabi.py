@@ -106,5 +106,5 @@ def last_launch_info():
     buf = (C.c_int32 * 16)()
     check(load().ntm_b200_last_launch_info(buf), "last_launch_info")
     keys = ("tensor_path", "sequences_resident", "ctas", "cluster_size", "ks_ctrl", "kw_ctrl", "ks_heads",
-            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta")
+            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta", "xproj_tensor_path")
     return dict(zip(keys, list(buf)))

@@ -39,6 +39,7 @@
 #include "ntm_b200.h"
 #include "ntm_b200_params.h"
 #include "ntm_b200_xproj.cuh"
+#include "ntm_b200_xproj_tc.cuh"
 
 using namespace ntm_b200;
 
@@ -454,8 +455,16 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   }
   // hoisted x-projection: xw[b,t,:] = x[b,t,:] @ W_lstm0[0:D,:] + b_lstm0
   float* xw = reinterpret_cast<float*>(wsb + ws.off_xw);
-  st = ntm_b200::launch_xproj(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
-                              (long long)batch * steps, shape->input_dim, 4 * C, stream);
+  // tensor-core kernel (tcgen05, weight tile resident in TMEM + SMEM); fp32 SIMT kernel for shapes it
+  // does not cover or when NTM_B200_DISABLE_TC is set
+  st = -1;
+  if (getenv("NTM_B200_DISABLE_TC") == nullptr)
+    st = ntm_b200::launch_xproj_tc(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
+                                   (long long)batch * steps, shape->input_dim, 4 * C, di.nsm, stream);
+  g_last_info[12] = (st == 0) ? 1 : 0;
+  if (st < 0)
+    st = ntm_b200::launch_xproj(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
+                                (long long)batch * steps, shape->input_dim, 4 * C, stream);
   g_launches++;
   if (st) return set_cuda_error(cudaGetLastError(), "xproj");
 
