@@ -150,6 +150,7 @@ def test_c2_tracker_full_config(gemm_path):
     info = _cabi.last_launch_info()
     assert info["tensor_path"] == (1 if gemm_path == "tensor" else 0), info
     assert info["sequences_resident"] == 64 and info["teams"] == 1 and info["cluster_size"] == 2
+    assert info["xproj_tensor_path"] == (1 if gemm_path == "tensor" else 0)
     assert max(errs.values()) <= TOL, errs
 
 
@@ -248,6 +249,26 @@ def test_host_inputs_round_trip():
     assert isinstance(out, np.ndarray) and out.shape == (4, 7, 4)
     _, rl, _ = O.run_sequence(params, s, x)
     assert maxerr(logits, rl) <= TOL
+
+
+def test_host_pipelined_chunks_match_device_call():
+    """Large host-resident batches are split into chunks whose H2D copy overlaps compute;
+    sequences are independent, so the result must equal the single device-resident call."""
+    kw, _, _ = O.CONFIGS["c1_copy"]
+    s = O.NTMShape(**kw)
+    params = O.init_params(s, 81, 0.05)
+    B, T = 2400, 3                                   # 148 resident -> 4 chunks of 600
+    x = O.copy_task_inputs(B, T, 3, 82)
+    trk = make_tracker(s, params, T)
+    trk.host_chunks = 4                              # opt-in (off by default)
+    assert trk._pipeline_chunks(B, T) == 4
+    out_h, log_h = trk(x)
+    st_h = {k: v.clone() for k, v in trk.final_state.items()}
+    out_d, log_d = trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    assert maxerr(log_h, to_np(log_d)) <= 1e-6 and maxerr(out_h, to_np(out_d)) <= 1e-6
+    for k in st_h:
+        assert maxerr(to_np(st_h[k]), to_np(trk.final_state[k])) <= 1e-6, k
 
 
 def test_degenerate_state_no_nan():
