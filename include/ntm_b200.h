@@ -133,6 +133,48 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
                              float* debug_taps, void* workspace, int64_t workspace_bytes,
                              void* stream);
 
+/* Training-mode history: what the backward pass needs from the forward pass (the reference gets
+ * it from TensorFlow's while_loop gradient machinery, `swap_memory=True`,
+ * ntm_tracker_new.py:34-40).  Every pointer is an optional caller-owned device buffer:
+ *   M_prev   [T, B, N, M]    memory entering step t
+ *   w_prev   [T, B, R+W, N]  weightings entering step t
+ *   params   [T, B, PO4]     raw (pre-activation) head parameters + logits of step t,
+ *                            PO4 = round_up(P + O, 4), layout of ntm_cell.py:126-130 then logits
+ *   z        [T, B, L, 4, C] LSTM gate pre-activations i, j, f, o of step t
+ *   c, h     [T+1, B, L, C]  LSTM cell / hidden state: slot 0 = initial, slot t+1 = after step t
+ *   read     [T+1, B, R*M]   read vectors: slot 0 = initial, slot t+1 = produced by step t */
+typedef struct ntm_b200_history {
+  float* M_prev;
+  float* w_prev;
+  float* params;
+  float* z;
+  float* c;
+  float* h;
+  float* read;
+} ntm_b200_history;
+
+/* ntm_b200_forward_seq that also records `history` (may be NULL = plain forward). */
+int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                                   const void* packed, int64_t batch, int64_t steps,
+                                   const float* inputs, const ntm_b200_state* state_in,
+                                   const ntm_b200_state* state_out, float* logits, float* outputs,
+                                   float* debug_taps, const ntm_b200_history* history,
+                                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One reverse-time step of the backward pass through the memory / addressing part of the cell
+ * (everything between the head-parameter projection and the memory: ntm_cell.py:133-215,
+ * ops.py:135-242) for `batch` sequences.  The reference obtains this from tf.gradients of the
+ * unrolled graph (direct_offset_output.py:611-613).  Inputs: the recorded history of that step
+ * (M_prev [B,N,M], w_prev [B,H,N], raw_params [B,PO4]) and the upstream gradients d_read [B,R,M]
+ * (w.r.t. the read vectors the step produced), d_w [B,H,N] (w.r.t. the weightings it produced)
+ * and dM [B,N,M] (w.r.t. the memory it produced).  Outputs: dM is overwritten with the gradient
+ * w.r.t. M_prev; d_w_prev [B,H,N]; d_raw_params [B,PO4] (logit slots zeroed).  The dense
+ * projections' gradients are plain GEMMs and stay with the caller. */
+int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* shape, int64_t batch, const float* M_prev,
+                                      const float* w_prev, const float* raw_params,
+                                      const float* d_read, const float* d_w, float* dM,
+                                      float* d_w_prev, float* d_raw_params, void* stream);
+
 /* NTMCell.__call__ (ntm_cell.py:53-253): one step, inputs [B,D], logits/outputs
  * [B,O].  The serve path's unit of work (test_tracker.py:284-299). */
 int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weights,

@@ -13,5 +13,6 @@ _cabi.load()   # no library -> RuntimeError here, never a silent fallback
 
 from .ntm_cell import NTMCell, random_uniform_initializer  # noqa: E402
 from .ntm_tracker_new import LoopNTMTracker  # noqa: E402
+from .training import NTMTrainer  # noqa: E402
 
-__all__ = ["NTMCell", "LoopNTMTracker", "random_uniform_initializer"]
+__all__ = ["NTMCell", "LoopNTMTracker", "NTMTrainer", "random_uniform_initializer"]

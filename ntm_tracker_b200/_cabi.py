@@ -36,6 +36,10 @@ class State(C.Structure):
                 ("stride_controller_state", C.c_int64)]
 
 
+class History(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("M_prev", "w_prev", "params", "z", "c", "h", "read")]
+
+
 class Plan(C.Structure):
     _fields_ = [("cluster_size", C.c_int32), ("rows_per_cta", C.c_int32),
                 ("sequences_resident", C.c_int32), ("threads_per_cta", C.c_int32),
@@ -56,6 +60,11 @@ SYMBOLS = {
                                          C.c_int64, C.c_int64, C.c_void_p, C.POINTER(State),
                                          C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p]),
+    "ntm_b200_forward_seq_train": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p,
+                                               C.c_int64, C.c_int64, C.c_void_p, C.POINTER(State),
+                                               C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.POINTER(History), C.c_void_p, C.c_int64, C.c_void_p]),
+    "ntm_b200_memory_backward_step": (C.c_int32, [C.POINTER(Shape), C.c_int64] + [C.c_void_p] * 9),
     "ntm_b200_step": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p, C.c_int64,
                                   C.c_void_p, C.POINTER(State), C.POINTER(State), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -410,6 +410,16 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
                              const ntm_b200_state* state_out, float* logits, float* outputs,
                              float* debug_taps, void* workspace, int64_t workspace_bytes,
                              void* stream_v) {
+  return ntm_b200_forward_seq_train(shape, weights, packed, batch, steps, inputs, state_in, state_out, logits,
+                                    outputs, debug_taps, nullptr, workspace, workspace_bytes, stream_v);
+}
+
+int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                                   const void* packed, int64_t batch, int64_t steps,
+                                   const float* inputs, const ntm_b200_state* state_in,
+                                   const ntm_b200_state* state_out, float* logits, float* outputs,
+                                   float* debug_taps, const ntm_b200_history* history,
+                                   void* workspace, int64_t workspace_bytes, void* stream_v) {
   if (!shape || !weights || !packed || !inputs || !logits || !workspace) return NTM_B200_ERR_NULL_POINTER;
   int st = check_state(state_in);
   if (st) return st;
@@ -496,6 +506,10 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
   p.dsM = state_out->stride_M; p.dsw = state_out->stride_w; p.dsread = state_out->stride_read;
   p.dsctrl = state_out->stride_controller_state;
   p.logits = logits; p.outputs = outputs; p.dbg = debug_taps; p.dbgStride = hp.debug_floats;
+  if (history != nullptr) {
+    p.hM = history->M_prev; p.hW = history->w_prev; p.hP = history->params; p.hZ = history->z;
+    p.hC = history->c; p.hH = history->h; p.hRead = history->read;
+  }
   p.cst = reinterpret_cast<float*>(wsb + ws.off_cst); p.cst_ts = ws.cst_ts;
   p.partA = reinterpret_cast<float*>(wsb + ws.off_partA); p.partA_ts = ws.partA_ts;
   p.partC = reinterpret_cast<float*>(wsb + ws.off_partC); p.partC_ts = ws.partC_ts;

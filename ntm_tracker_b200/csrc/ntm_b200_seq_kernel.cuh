@@ -348,12 +348,16 @@ __device__ __forceinline__ void lstm_phase(const KParams& p, int l, int Gcur, in
     const float zj = __shfl_sync(0xffffffffu, v, gl + 1);
     const float zf = __shfl_sync(0xffffffffu, v, gl + 2);
     const float zo = __shfl_sync(0xffffffffu, v, gl + 3);
+    if (ok && p.hZ != nullptr)   // pre-activation of gate q (training history)
+      p.hZ[((((size_t)t * p.B + (b0 + b)) * p.L + l) * 4 + q) * C + u] = v;
     if (ok && q == 0) {
       float* cp = cst + ((size_t)b * p.L + l) * C + u;
       const float c_prev = __ldcg(cp);
       const float c_new = c_prev * sigmoid_f(zf) + sigmoid_f(zi) * tanhf(zj);
       const float h_new = tanhf(c_new) * sigmoid_f(zo);
       *cp = c_new;
+      if (p.hC != nullptr) p.hC[(((size_t)(t + 1) * p.B + (b0 + b)) * p.L + l) * C + u] = c_new;
+      if (p.hH != nullptr) p.hH[(((size_t)(t + 1) * p.B + (b0 + b)) * p.L + l) * C + u] = h_new;
       act[l][(size_t)b * p.actK[l] + (p.actK[l] - C) + u] = h_new;
       if (l + 1 < p.L) act[l + 1][(size_t)b * p.actK[l + 1] + u] = h_new;
     }
@@ -428,8 +432,27 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     const float4* pc4 = reinterpret_cast<const float4*>(partC + (size_t)gslot * p.gC.NCs);
     const float4* b4 = reinterpret_cast<const float4*>(p.bC);
     const size_t slab4 = (size_t)p.gC.Gpad * p.gC.NCs / 4;
-    for (int q4 = tid; q4 < p.PO4 / 4; q4 += NT)
-      reinterpret_cast<float4*>(raw)[q4] = sum_slabs4(pc4 + q4, slab4, p.gC.KS, __ldg(b4 + q4));
+    float4* hp4 = (p.hP != nullptr && crank == 0)
+                      ? reinterpret_cast<float4*>(p.hP + ((size_t)t * p.B + bglob) * p.PO4) : nullptr;
+    for (int q4 = tid; q4 < p.PO4 / 4; q4 += NT) {
+      const float4 v4 = sum_slabs4(pc4 + q4, slab4, p.gC.KS, __ldg(b4 + q4));
+      reinterpret_cast<float4*>(raw)[q4] = v4;
+      if (hp4) hp4[q4] = v4;
+    }
+  }
+  if (p.hW != nullptr && crank == 0) {   // weightings entering this step
+    float* hw = p.hW + ((size_t)t * p.B + bglob) * H * N;
+    for (int i = tid; i < H * N; i += NT) {
+      const int h = i / N, n = i - h * N;
+      hw[i] = wprev[h * Npad + n];
+    }
+  }
+  if (p.hM != nullptr) {                 // memory entering this step (this CTA's rows)
+    float* hm = p.hM + (((size_t)t * p.B + bglob) * N + row0) * M;
+    for (int i = tid; i < nrows * M; i += NT) {
+      const int r = i / M, d = i - r * M;
+      hm[i] = Ms[r * M4 + d];
+    }
   }
   __syncthreads();
   mark_slot(prow, tmark, 15);
@@ -756,6 +779,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     }
     act0[(size_t)gslot * p.actK[0] + i] = s;              // next step's controller input
     if (last) p.dread[(size_t)bglob * p.dsread + i] = s;
+    if (p.hRead != nullptr) p.hRead[((size_t)(t + 1) * p.B + bglob) * (R * M) + i] = s;
   }
   wcur ^= 1;
   mark_slot(prow, tmark, 14);
@@ -839,12 +863,19 @@ __global__ void NTM_KERNEL_BOUNDS ntm_seq_kernel(const KParams p) {
       }
       if (crank == 0) {
         const float* srcr = p.sread + (size_t)bglob * p.ssread;
-        for (int i = tid; i < R * p.M; i += NT) act[0][(size_t)gslot * p.actK[0] + i] = __ldg(srcr + i);
+        for (int i = tid; i < R * p.M; i += NT) {
+          const float v = __ldg(srcr + i);
+          act[0][(size_t)gslot * p.actK[0] + i] = v;
+          if (p.hRead != nullptr) p.hRead[(size_t)bglob * (R * p.M) + i] = v;
+        }
         const float* srcc = p.sctrl + (size_t)bglob * p.ssctrl;
         for (int i = tid; i < p.L * p.C; i += NT) {
           const int l = i / p.C, u = i - l * p.C;
-          cst[((size_t)gslot * p.L + l) * p.C + u] = __ldg(srcc + (size_t)l * 2 * p.C + u);
-          act[l][(size_t)gslot * p.actK[l] + (p.actK[l] - p.C) + u] = __ldg(srcc + (size_t)l * 2 * p.C + p.C + u);
+          const float c0 = __ldg(srcc + (size_t)l * 2 * p.C + u), h0 = __ldg(srcc + (size_t)l * 2 * p.C + p.C + u);
+          cst[((size_t)gslot * p.L + l) * p.C + u] = c0;
+          act[l][(size_t)gslot * p.actK[l] + (p.actK[l] - p.C) + u] = h0;
+          if (p.hC != nullptr) p.hC[((size_t)bglob * p.L + l) * p.C + u] = c0;
+          if (p.hH != nullptr) p.hH[((size_t)bglob * p.L + l) * p.C + u] = h0;
         }
       }
       __syncthreads();

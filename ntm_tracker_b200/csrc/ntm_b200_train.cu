@@ -1,0 +1,546 @@
+// ntm_b200_train.cu -- reverse-time step of the NTM memory / addressing backward pass.
+//
+// The reference trains through tf.gradients of the unrolled while_loop
+// (direct_offset_output.py:611-626); TensorFlow derives the backward graph op by op.  Here the
+// backward of everything between the head-parameter projection and the memory (K3-K9 of
+// column-normalised similarity, beta-softmax, gate, circular shift, sharpening,
+// erase/add write, weighted read -- ntm_cell.py:133-215, ops.py:135-242) is ONE kernel per
+// timestep, one CTA per sequence.  The dense projections' gradients are plain GEMMs and are left
+// to the caller (ntm_tracker_b200/training.py).
+//
+// Per sequence and step, given  dL/dM_t, dL/dw_t, dL/dread_t  it recomputes the forward
+// quantities from the recorded history (M_{t-1}, w_{t-1}, raw head parameters) and returns
+// dL/dM_{t-1} (in place), dL/dw_{t-1} and dL/d(raw head parameters).
+//
+// Mapping: threads form a (column-chunk x row-group) tile over the N x M memory, which streams
+// from HBM/L2 as coalesced float4 rows; row reductions go warp-shuffle -> shared memory, column
+// reductions go registers -> shared memory, both summed in fixed order (deterministic).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "ntm_b200.h"
+#include "ntm_b200_params.h"
+
+namespace ntm_b200 {
+namespace train {
+
+constexpr int NT = 512;
+constexpr int NWARP = NT / 32;
+
+struct BwdParams {
+  int N, M, M4, MC, Np, S, shift0, R, W, H, P, PO4, write_first;
+  int TPR, RG, TW;            // threads per row (multiple of 32), row groups, warps per row
+  const float* M_prev;        // [B, N, M]
+  const float* w_prev;        // [B, H, N]
+  const float* raw;           // [B, PO4]
+  const float* d_read;        // [B, R, M]
+  const float* d_w;           // [B, H, N]
+  float* dM;                  // [B, N, M] in: dL/dM_t, out: dL/dM_{t-1}
+  float* d_w_prev;            // [B, H, N]
+  float* d_raw;               // [B, PO4]
+  // shared-memory offsets (floats)
+  int oK, oKhat, oKc, oE, oA, oCn, oCok, oDkh, oDe, oDa, oCt;
+  int oSim, oWc, oWg, oWt, oPw, oW, oDw, oDsim, oWp;
+  int oRow, oCol, oSc;
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float4 ld4(const float* base, int M, int d0) {
+  // row pointer `base`, columns d0..d0+3 of a row of M valid floats (vector load when aligned)
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) return *reinterpret_cast<const float4*>(base + d0);
+  if (d0 + 0 < M) v.x = base[d0 + 0];
+  if (d0 + 1 < M) v.y = base[d0 + 1];
+  if (d0 + 2 < M) v.z = base[d0 + 2];
+  if (d0 + 3 < M) v.w = base[d0 + 3];
+  return v;
+}
+__device__ __forceinline__ void st4(float* base, int M, int d0, const float4& v) {
+  if (((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) { *reinterpret_cast<float4*>(base + d0) = v; return; }
+  if (d0 + 0 < M) base[d0 + 0] = v.x;
+  if (d0 + 1 < M) base[d0 + 1] = v.y;
+  if (d0 + 2 < M) base[d0 + 2] = v.z;
+  if (d0 + 3 < M) base[d0 + 3] = v.w;
+}
+
+template <int R, int W>
+__global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) {
+  constexpr int H = R + W;
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const int N = q.N, M = q.M, M4 = q.M4, MC = q.MC, Np = q.Np, S = q.S;
+  const int c = tid % q.TPR, rg = tid / q.TPR;      // column chunk, row group
+  const bool cvalid = c < MC && rg < q.RG;
+  const int wrow = (tid % q.TPR) >> 5;              // warp index within the row
+  float* kS = sm + q.oK;   float* khat = sm + q.oKhat; float* kc = sm + q.oKc;
+  float* eS = sm + q.oE;   float* aS = sm + q.oA;      float* cn = sm + q.oCn;  float* cok = sm + q.oCok;
+  float* dkh = sm + q.oDkh; float* deS = sm + q.oDe;   float* daS = sm + q.oDa; float* ct = sm + q.oCt;
+  float* sim = sm + q.oSim; float* wc = sm + q.oWc; float* wg = sm + q.oWg; float* wt = sm + q.oWt;
+  float* pw = sm + q.oPw;   float* wv = sm + q.oW;  float* dw = sm + q.oDw; float* dsim = sm + q.oDsim;
+  float* wp = sm + q.oWp;
+  float* rowbuf = sm + q.oRow;                       // [N][TW][H]
+  float* colbuf = sm + q.oCol;                       // [RG][NQ][M4]
+  float* sc = sm + q.oSc;                            // scalars
+  float* sBeta = sc, *sG = sc + H, *sGam = sc + 2 * H, *sRs = sc + 3 * H, *sKok = sc + 4 * H,
+        *sSw = sc + 5 * H, *sDsw = sc + 5 * H + H * SMAX, *sDbeta = sc + 5 * H + 2 * H * SMAX,
+        *sDg = sDbeta + H, *sDgam = sDg + H, *sSum = sDgam + H;
+  const float* Mb = q.M_prev + (size_t)b * N * M;
+  float* dMb = q.dM + (size_t)b * N * M;
+  const float* raw = q.raw + (size_t)b * q.PO4;
+  const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
+            offE = offGam + H, offA = offE + M * W;
+
+  // ---- (1) activations of the recorded raw head parameters ----
+  for (int i = tid; i < H * M4; i += NT) {
+    const int h = i / M4, d = i - h * M4;
+    kS[i] = (d < M) ? tanhf(raw[h * M + d]) : 0.0f;
+  }
+  for (int i = tid; i < W * M4; i += NT) {
+    const int h = i / M4, d = i - h * M4;
+    eS[i] = (d < M) ? sigmoid_f(raw[offE + h * M + d]) : 0.0f;
+    aS[i] = (d < M) ? tanhf(raw[offA + h * M + d]) : 0.0f;
+  }
+  if (tid < H) {
+    sBeta[tid] = softplus_f(raw[offBeta + tid]);
+    sG[tid] = sigmoid_f(raw[offG + tid]);
+    sGam[tid] = 1.0f + softplus_f(raw[offGam + tid]);
+    float mx = raw[offS + tid * S];
+    for (int i = 1; i < S; ++i) mx = fmaxf(mx, raw[offS + tid * S + i]);
+    float sum = 0.0f;
+    for (int i = 0; i < S; ++i) { sSw[tid * SMAX + i] = expf(raw[offS + tid * S + i] - mx); sum += sSw[tid * SMAX + i]; }
+    for (int i = 0; i < S; ++i) sSw[tid * SMAX + i] /= sum;
+  }
+  for (int i = tid; i < H * N; i += NT) {
+    const int h = i / N, n = i - h * N;
+    wp[h * Np + n] = q.w_prev[(size_t)b * H * N + i];
+    dw[h * Np + n] = q.d_w[(size_t)b * H * N + i];
+  }
+  __syncthreads();
+
+  // ---- (2) F1: column sums of squares -> cn ----
+  {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cvalid)
+      for (int n = rg; n < N; n += q.RG) {
+        const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
+        acc.x = fmaf(m.x, m.x, acc.x); acc.y = fmaf(m.y, m.y, acc.y);
+        acc.z = fmaf(m.z, m.z, acc.z); acc.w = fmaf(m.w, m.w, acc.w);
+      }
+    if (cvalid) *reinterpret_cast<float4*>(colbuf + (size_t)rg * M4 + 4 * c) = acc;
+  }
+  __syncthreads();
+  for (int d = tid; d < M4; d += NT) {
+    float s = 0.0f;
+    for (int r2 = 0; r2 < q.RG; ++r2) s += colbuf[(size_t)r2 * M4 + d];
+    cn[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+    cok[d] = (s > 1e-12f) ? 1.0f : 0.0f;
+  }
+  for (int h = warp; h < H; h += NWARP) {
+    float s = 0.0f;
+    for (int d = lane; d < M; d += 32) s = fmaf(kS[h * M4 + d], kS[h * M4 + d], s);
+    s = warp_sum(s);
+    if (lane == 0) { sRs[h] = 1.0f / sqrtf(fmaxf(s, 1e-12f)); sKok[h] = (s > 1e-12f) ? 1.0f : 0.0f; }
+  }
+  __syncthreads();
+  for (int i = tid; i < H * M4; i += NT) {
+    const int h = i / M4, d = i - h * M4;
+    khat[i] = kS[i] * sRs[h];
+    kc[i] = khat[i] * cn[d];
+  }
+  __syncthreads();
+
+  // ---- (3) F2: similarities (row reductions) ----
+  for (int n0 = 0; n0 < N; n0 += q.RG) {
+    const int n = n0 + rg;
+    float part[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) part[h] = 0.0f;
+    if (cvalid && n < N) {
+      const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = dot4(m, *reinterpret_cast<const float4*>(kc + h * M4 + 4 * c));
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) part[h] = warp_sum(part[h]);
+    if (lane == 0 && rg < q.RG && n < N) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) rowbuf[((size_t)n * q.TW + wrow) * H + h] = part[h];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < H * N; i += NT) {
+    const int h = i / N, n = i - h * N;
+    float s = 0.0f;
+    for (int w2 = 0; w2 < q.TW; ++w2) s += rowbuf[((size_t)n * q.TW + w2) * H + h];
+    sim[h * Np + n] = s;
+  }
+  __syncthreads();
+
+  // ---- (4) forward weightings, one warp per head (ntm_cell.py:140-176) ----
+  for (int h = warp; h < H; h += NWARP) {
+    const float beta = sBeta[h], g = sG[h], gamma = sGam[h];
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, sim[h * Np + n] * beta);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int n = lane; n < N; n += 32) { const float e = expf(sim[h * Np + n] * beta - mx); wc[h * Np + n] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int n = lane; n < N; n += 32) {
+      const float v = wc[h * Np + n] / sum;
+      wc[h * Np + n] = v;
+      wg[h * Np + n] = v * g + wp[h * Np + n] * (1.0f - g);
+    }
+    __syncwarp();
+    float psum = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      float conv = 0.0f;
+      for (int s = 0; s < S; ++s) {
+        int idx = n + q.shift0 + s;
+        idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+        conv = fmaf(sSw[h * SMAX + s], wg[h * Np + idx], conv);
+      }
+      const float pv = exp2f(gamma * log2f(conv));
+      wt[h * Np + n] = conv;
+      pw[h * Np + n] = pv;
+      psum += pv;
+    }
+    psum = warp_sum(psum);
+    const float den = psum + 1e-3f;
+    if (lane == 0) sSum[h] = den;
+    for (int n = lane; n < N; n += 32) wv[h * Np + n] = pw[h * Np + n] / den;
+  }
+  __syncthreads();
+
+  // ---- (5) B1: read + write backward; row sums d_w(read|write), column sums d_e, d_a ----
+  {
+    float4 dr4[R], e4[W], a4[W], dea[W], daa[W];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      dr4[r] = cvalid ? ld4(q.d_read + ((size_t)b * R + r) * M, M, 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < W; ++h) {
+      e4[h] = cvalid ? *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a4[h] = cvalid ? *reinterpret_cast<const float4*>(aS + h * M4 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dea[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      daa[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int n0 = 0; n0 < N; n0 += q.RG) {
+      const int n = n0 + rg;
+      float part[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = 0.0f;
+      if (cvalid && n < N) {
+        const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
+        const float4 dmn = ld4(dMb + (size_t)n * M, M, 4 * c);
+        float ww[W];
+        float4 F[W];
+        float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < W; ++h) {
+          ww[h] = wv[(R + h) * Np + n];
+          F[h] = make_float4(1.0f - ww[h] * e4[h].x, 1.0f - ww[h] * e4[h].y, 1.0f - ww[h] * e4[h].z, 1.0f - ww[h] * e4[h].w);
+          E.x *= F[h].x; E.y *= F[h].y; E.z *= F[h].z; E.w *= F[h].w;
+          A.x = fmaf(ww[h], a4[h].x, A.x); A.y = fmaf(ww[h], a4[h].y, A.y);
+          A.z = fmaf(ww[h], a4[h].z, A.z); A.w = fmaf(ww[h], a4[h].w, A.w);
+        }
+        const float4 mn = make_float4(fmaf(m.x, E.x, A.x), fmaf(m.y, E.y, A.y), fmaf(m.z, E.z, A.z), fmaf(m.w, E.w, A.w));
+        const float4 mu = q.write_first ? mn : m;
+        float4 dmu = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float wr = wv[r * Np + n];
+          dmu.x = fmaf(wr, dr4[r].x, dmu.x); dmu.y = fmaf(wr, dr4[r].y, dmu.y);
+          dmu.z = fmaf(wr, dr4[r].z, dmu.z); dmu.w = fmaf(wr, dr4[r].w, dmu.w);
+          part[r] = dot4(dr4[r], mu);
+        }
+        float4 dt = dmn;                                // dL/dM_t including the read path if write_first
+        if (q.write_first) { dt.x += dmu.x; dt.y += dmu.y; dt.z += dmu.z; dt.w += dmu.w; }
+        const float4 dE = make_float4(dt.x * m.x, dt.y * m.y, dt.z * m.z, dt.w * m.w);
+#pragma unroll
+        for (int h = 0; h < W; ++h) {
+          float4 pex = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+          for (int o = 0; o < W; ++o)
+            if (o != h) { pex.x *= F[o].x; pex.y *= F[o].y; pex.z *= F[o].z; pex.w *= F[o].w; }
+          const float4 dF = make_float4(dE.x * pex.x, dE.y * pex.y, dE.z * pex.z, dE.w * pex.w);
+          part[R + h] = dot4(dt, a4[h]) - dot4(dF, e4[h]);
+          dea[h].x -= dF.x * ww[h]; dea[h].y -= dF.y * ww[h]; dea[h].z -= dF.z * ww[h]; dea[h].w -= dF.w * ww[h];
+          daa[h].x = fmaf(dt.x, ww[h], daa[h].x); daa[h].y = fmaf(dt.y, ww[h], daa[h].y);
+          daa[h].z = fmaf(dt.z, ww[h], daa[h].z); daa[h].w = fmaf(dt.w, ww[h], daa[h].w);
+        }
+        float4 dout = make_float4(dt.x * E.x, dt.y * E.y, dt.z * E.z, dt.w * E.w);
+        if (!q.write_first) { dout.x += dmu.x; dout.y += dmu.y; dout.z += dmu.z; dout.w += dmu.w; }
+        st4(dMb + (size_t)n * M, M, 4 * c, dout);
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[h] = warp_sum(part[h]);
+      if (lane == 0 && rg < q.RG && n < N) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) rowbuf[((size_t)n * q.TW + wrow) * H + h] = part[h];
+      }
+    }
+    if (cvalid) {
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        *reinterpret_cast<float4*>(colbuf + ((size_t)rg * 2 * W + h) * M4 + 4 * c) = dea[h];
+        *reinterpret_cast<float4*>(colbuf + ((size_t)rg * 2 * W + W + h) * M4 + 4 * c) = daa[h];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < H * N; i += NT) {               // total dL/dw_t
+    const int h = i / N, n = i - h * N;
+    float s = dw[h * Np + n];
+    for (int w2 = 0; w2 < q.TW; ++w2) s += rowbuf[((size_t)n * q.TW + w2) * H + h];
+    dw[h * Np + n] = s;
+  }
+  for (int i = tid; i < W * M4; i += NT) {
+    const int h = i / M4, d = i - h * M4;
+    float se = 0.0f, sa = 0.0f;
+    for (int r2 = 0; r2 < q.RG; ++r2) {
+      se += colbuf[((size_t)r2 * 2 * W + h) * M4 + d];
+      sa += colbuf[((size_t)r2 * 2 * W + W + h) * M4 + d];
+    }
+    deS[i] = se;
+    daS[i] = sa;
+  }
+  __syncthreads();
+
+  // ---- (6) weightings backward, one warp per head ----
+  for (int h = warp; h < H; h += NWARP) {
+    const float beta = sBeta[h], g = sG[h], gamma = sGam[h], den = sSum[h];
+    float* dwt = dsim + h * Np;                          // scratch: dL/dw~, later dL/dsim
+    float t1 = 0.0f;
+    for (int n = lane; n < N; n += 32) t1 = fmaf(dw[h * Np + n], pw[h * Np + n], t1);
+    t1 = warp_sum(t1);
+    float dgam = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      const float dp = dw[h * Np + n] / den - t1 / (den * den);
+      const float x = wt[h * Np + n], pv = pw[h * Np + n];
+      float d = 0.0f;
+      if (x > 0.0f) {
+        d = dp * gamma * pv / x;
+        dgam = fmaf(dp * pv, logf(x), dgam);
+      }
+      dwt[n] = d;
+    }
+    dgam = warp_sum(dgam);
+    __syncwarp();
+    float dgate = 0.0f, t2 = 0.0f;
+    float dsw[SMAX];
+#pragma unroll
+    for (int s = 0; s < SMAX; ++s) dsw[s] = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      float dwg = 0.0f;
+#pragma unroll
+      for (int s = 0; s < SMAX; ++s) {
+        if (s < S) {
+          const int off = q.shift0 + s;
+          int src = n - off;                             // w~[src] reads wg[(src + off) mod N] = wg[n]
+          src = src < 0 ? src + N : (src >= N ? src - N : src);
+          dwg = fmaf(sSw[h * SMAX + s], dwt[src], dwg);
+          int idx = n + off;
+          idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+          dsw[s] = fmaf(dwt[n], wg[h * Np + idx], dsw[s]);
+        }
+      }
+      const float wcv = wc[h * Np + n], wpv = wp[h * Np + n];
+      dgate = fmaf(dwg, wcv - wpv, dgate);
+      q.d_w_prev[(size_t)b * H * N + h * N + n] = (1.0f - g) * dwg;
+      const float dwc = g * dwg;
+      pw[h * Np + n] = dwc;                              // pw is dead: reuse for dL/dwc
+      t2 = fmaf(dwc, wcv, t2);
+    }
+    dgate = warp_sum(dgate);
+    t2 = warp_sum(t2);
+#pragma unroll
+    for (int s = 0; s < SMAX; ++s) dsw[s] = warp_sum(dsw[s]);
+    __syncwarp();
+    float dbeta = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      const float dx = wc[h * Np + n] * (pw[h * Np + n] - t2);
+      dbeta = fmaf(dx, sim[h * Np + n], dbeta);
+      dwt[n] = beta * dx;                                // dL/dsim
+    }
+    dbeta = warp_sum(dbeta);
+    if (lane == 0) {
+      sDbeta[h] = dbeta; sDg[h] = dgate; sDgam[h] = dgam;
+      float dot = 0.0f;
+      for (int s = 0; s < S; ++s) dot = fmaf(dsw[s], sSw[h * SMAX + s], dot);
+      for (int s = 0; s < S; ++s) sDsw[h * SMAX + s] = sSw[h * SMAX + s] * (dsw[s] - dot);   // through the softmax
+    }
+  }
+  __syncthreads();
+
+  // ---- (7) B2: column sums dL/dkhat and the column-norm term ----
+  {
+    constexpr int NQ = H + 1;
+    float4 acc[NQ], kh4[H], cn4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cvalid) {
+      cn4 = *reinterpret_cast<const float4*>(cn + 4 * c);
+#pragma unroll
+      for (int h = 0; h < H; ++h) kh4[h] = *reinterpret_cast<const float4*>(khat + h * M4 + 4 * c);
+      for (int n = rg; n < N; n += q.RG) {
+        const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
+        float4 dmh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float ds = dsim[h * Np + n];
+          dmh.x = fmaf(ds, kh4[h].x, dmh.x); dmh.y = fmaf(ds, kh4[h].y, dmh.y);
+          dmh.z = fmaf(ds, kh4[h].z, dmh.z); dmh.w = fmaf(ds, kh4[h].w, dmh.w);
+          acc[h].x = fmaf(ds, m.x * cn4.x, acc[h].x); acc[h].y = fmaf(ds, m.y * cn4.y, acc[h].y);
+          acc[h].z = fmaf(ds, m.z * cn4.z, acc[h].z); acc[h].w = fmaf(ds, m.w * cn4.w, acc[h].w);
+        }
+        acc[H].x = fmaf(dmh.x, m.x, acc[H].x); acc[H].y = fmaf(dmh.y, m.y, acc[H].y);
+        acc[H].z = fmaf(dmh.z, m.z, acc[H].z); acc[H].w = fmaf(dmh.w, m.w, acc[H].w);
+      }
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) *reinterpret_cast<float4*>(colbuf + ((size_t)rg * NQ + i) * M4 + 4 * c) = acc[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < NQ * M4; i += NT) {
+      const int qq = i / M4, d = i - qq * M4;
+      float s = 0.0f;
+      for (int r2 = 0; r2 < q.RG; ++r2) s += colbuf[((size_t)r2 * NQ + qq) * M4 + d];
+      if (qq < H) dkh[qq * M4 + d] = s; else ct[d] = s;
+    }
+    __syncthreads();
+  }
+
+  // ---- (8) B3: dL/dM_{t-1} += similarity path (through the column normalisation) ----
+  if (cvalid) {
+    const float4 cn4 = *reinterpret_cast<const float4*>(cn + 4 * c);
+    const float4 ok4 = *reinterpret_cast<const float4*>(cok + 4 * c);
+    const float4 ct4 = *reinterpret_cast<const float4*>(ct + 4 * c);
+    float4 kh4[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) kh4[h] = *reinterpret_cast<const float4*>(khat + h * M4 + 4 * c);
+    const float4 c3 = make_float4(ok4.x * cn4.x * cn4.x * cn4.x * ct4.x, ok4.y * cn4.y * cn4.y * cn4.y * ct4.y,
+                                  ok4.z * cn4.z * cn4.z * cn4.z * ct4.z, ok4.w * cn4.w * cn4.w * cn4.w * ct4.w);
+    for (int n = rg; n < N; n += q.RG) {
+      const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
+      float4 d = ld4(dMb + (size_t)n * M, M, 4 * c);
+      float4 dmh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float ds = dsim[h * Np + n];
+        dmh.x = fmaf(ds, kh4[h].x, dmh.x); dmh.y = fmaf(ds, kh4[h].y, dmh.y);
+        dmh.z = fmaf(ds, kh4[h].z, dmh.z); dmh.w = fmaf(ds, kh4[h].w, dmh.w);
+      }
+      d.x += cn4.x * dmh.x - m.x * c3.x; d.y += cn4.y * dmh.y - m.y * c3.y;
+      d.z += cn4.z * dmh.z - m.z * c3.z; d.w += cn4.w * dmh.w - m.w * c3.w;
+      st4(dMb + (size_t)n * M, M, 4 * c, d);
+    }
+  }
+
+  // ---- (9) back through the activations -> dL/d(raw head parameters) ----
+  float* draw = q.d_raw + (size_t)b * q.PO4;
+  for (int h = warp; h < H; h += NWARP) {             // key: through the l2 normalisation, then tanh
+    float dot = 0.0f;
+    for (int d = lane; d < M; d += 32) dot = fmaf(khat[h * M4 + d], dkh[h * M4 + d], dot);
+    dot = warp_sum(dot) * sKok[h];
+    for (int d = lane; d < M; d += 32) {
+      const float k = kS[h * M4 + d];
+      const float dk = sRs[h] * (dkh[h * M4 + d] - khat[h * M4 + d] * dot);
+      draw[h * M + d] = dk * (1.0f - k * k);
+    }
+  }
+  for (int i = tid; i < W * M; i += NT) {
+    const int h = i / M, d = i - h * M;
+    const float e = eS[h * M4 + d], a = aS[h * M4 + d];
+    draw[offE + i] = deS[h * M4 + d] * e * (1.0f - e);
+    draw[offA + i] = daS[h * M4 + d] * (1.0f - a * a);
+  }
+  if (tid < H) {
+    draw[offBeta + tid] = sDbeta[tid] * sigmoid_f(raw[offBeta + tid]);
+    draw[offG + tid] = sDg[tid] * sG[tid] * (1.0f - sG[tid]);
+    draw[offGam + tid] = sDgam[tid] * sigmoid_f(raw[offGam + tid]);
+    for (int s = 0; s < S; ++s) draw[offS + tid * S + s] = sDsw[tid * SMAX + s];
+  }
+  for (int i = q.P + tid; i < q.PO4; i += NT) draw[i] = 0.0f;   // logit slots belong to the caller
+}
+
+typedef void (*BwdKernel)(const BwdParams);
+#define NTM_BK(R, W) mem_backward_kernel<R, W>
+static BwdKernel select_bwd(int R, int W) {
+  static const BwdKernel table[NTM_B200_MAX_READ_HEADS][NTM_B200_MAX_WRITE_HEADS] = {
+      {NTM_BK(1, 1), NTM_BK(1, 2), NTM_BK(1, 3)},
+      {NTM_BK(2, 1), NTM_BK(2, 2), NTM_BK(2, 3)},
+      {NTM_BK(3, 1), NTM_BK(3, 2), NTM_BK(3, 3)},
+      {NTM_BK(4, 1), NTM_BK(4, 2), NTM_BK(4, 3)}};
+  return table[R - 1][W - 1];
+}
+
+}  // namespace train
+}  // namespace ntm_b200
+
+extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_t batch, const float* M_prev,
+                                                 const float* w_prev, const float* raw_params,
+                                                 const float* d_read, const float* d_w, float* dM,
+                                                 float* d_w_prev, float* d_raw_params, void* stream) {
+  using namespace ntm_b200;
+  using namespace ntm_b200::train;
+  if (!s || !M_prev || !w_prev || !raw_params || !d_read || !d_w || !dM || !d_w_prev || !d_raw_params)
+    return NTM_B200_ERR_NULL_POINTER;
+  if (batch < 1 || s->mem_size < 1 || s->mem_dim < 1) return NTM_B200_ERR_BAD_SHAPE;
+  if (s->read_head_size < 1 || s->read_head_size > NTM_B200_MAX_READ_HEADS || s->write_head_size < 1 ||
+      s->write_head_size > NTM_B200_MAX_WRITE_HEADS)
+    return NTM_B200_ERR_UNSUPPORTED_HEADS;
+  if (s->shift_range < 0 || s->shift_range > NTM_B200_MAX_SHIFT_RANGE) return NTM_B200_ERR_BAD_SHIFT;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      major != 10) {
+    cudaGetLastError();
+    return NTM_B200_ERR_NO_DEVICE;
+  }
+  BwdParams q{};
+  const int R = s->read_head_size, W = s->write_head_size, H = R + W;
+  q.N = s->mem_size; q.M = s->mem_dim; q.M4 = (q.M + 3) / 4 * 4; q.MC = q.M4 / 4; q.Np = (q.N + 3) / 4 * 4;
+  q.S = 2 * s->shift_range + 1; q.shift0 = -((q.S + 1) / 2); q.R = R; q.W = W; q.H = H;
+  q.P = H * q.M + 3 * H + q.S * H + 2 * q.M * W;
+  q.PO4 = (q.P + s->output_dim + 3) / 4 * 4;
+  q.write_first = s->write_first ? 1 : 0;
+  q.TPR = std::min(NT, (q.MC + 31) / 32 * 32);
+  if (q.MC > NT) return NTM_B200_ERR_TOO_LARGE;
+  q.RG = NT / q.TPR; q.TW = q.TPR / 32;
+  q.M_prev = M_prev; q.w_prev = w_prev; q.raw = raw_params; q.d_read = d_read; q.d_w = d_w; q.dM = dM;
+  q.d_w_prev = d_w_prev; q.d_raw = d_raw_params;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
+  q.oK = take(H * q.M4); q.oKhat = take(H * q.M4); q.oKc = take(H * q.M4); q.oE = take(W * q.M4); q.oA = take(W * q.M4);
+  q.oCn = take(q.M4); q.oCok = take(q.M4); q.oDkh = take(H * q.M4); q.oDe = take(W * q.M4); q.oDa = take(W * q.M4);
+  q.oCt = take(q.M4);
+  q.oSim = take(H * q.Np); q.oWc = take(H * q.Np); q.oWg = take(H * q.Np); q.oWt = take(H * q.Np); q.oPw = take(H * q.Np);
+  q.oW = take(H * q.Np); q.oDw = take(H * q.Np); q.oDsim = take(H * q.Np); q.oWp = take(H * q.Np);
+  q.oRow = take(q.N * q.TW * H);
+  q.oCol = take(q.RG * std::max(2 * W, H + 1) * q.M4);
+  q.oSc = take(5 * H + 2 * H * SMAX + 4 * H);
+  const int smem = 4 * o;
+  if (smem > B200_SMEM_OPTIN) return NTM_B200_ERR_TOO_LARGE;
+  BwdKernel k = select_bwd(R, W);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return NTM_B200_ERR_CUDA;
+  }
+  k<<<(unsigned)batch, NT, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+}

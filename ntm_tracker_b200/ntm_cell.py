@@ -236,7 +236,7 @@ class NTMCell(object):
         return _cabi.State(*ptrs, *strides), keep
 
     # ------------------------------------------------------------------- run --
-    def _run(self, inputs, state, steps):
+    def _run(self, inputs, state, steps, history=None):
         """inputs [B, steps, D] float32 CUDA contiguous -> (logits, outputs, new_state, taps)."""
         lib = _cabi.load()
         if not torch.cuda.is_available():
@@ -278,10 +278,15 @@ class NTMCell(object):
         taps = None
         if self.debug:
             taps = torch.zeros(B, int(plan.debug_floats_per_sequence), dtype=torch.float32, device=dev)
-        _cabi.check(lib.ntm_b200_forward_seq(
+        hstruct = None
+        if history is not None:      # training mode: record what the backward pass needs
+            hstruct = _cabi.History(*[history[k].data_ptr() if history.get(k) is not None else None
+                                      for k, _ in _cabi.History._fields_])
+        _cabi.check(lib.ntm_b200_forward_seq_train(
             C.byref(shp), C.byref(wts), self._packed.data_ptr(), B, T, inputs.data_ptr(),
             C.byref(sin), C.byref(sout), logits.data_ptr(), outputs.data_ptr(),
-            taps.data_ptr() if taps is not None else None, ws.data_ptr(), ws.numel(), stream),
+            taps.data_ptr() if taps is not None else None,
+            C.byref(hstruct) if hstruct is not None else None, ws.data_ptr(), ws.numel(), stream),
             "forward_seq")
         self._last_ws = ws
         return logits, outputs, new_state, taps

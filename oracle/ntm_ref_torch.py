@@ -48,9 +48,10 @@ def batched_circular_convolution(t, kernel):
 
 
 class TorchRefNTM(object):
-    def __init__(self, shape: O.NTMShape, params):
+    def __init__(self, shape: O.NTMShape, params, dtype=torch.float32, requires_grad=False):
         self.s = shape
-        self.p = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in params.items()}
+        self.dtype = dtype
+        self.p = {k: torch.as_tensor(v).to(dtype).clone().requires_grad_(requires_grad) for k, v in params.items()}
 
     def zero_state(self, B):
         s, p = self.s, self.p
@@ -59,7 +60,8 @@ class TorchRefNTM(object):
         r = torch.tanh(p[O.SCOPE + "/init_state/read"])
         return {"M": torch.stack([M] * B, 0), "w": torch.stack([w] * B, 0),
                 "read": torch.stack([r] * B, 0),
-                "controller_state": torch.zeros(B, 2 * s.controller_hidden_size * s.controller_num_layers)}
+                "controller_state": torch.zeros(B, 2 * s.controller_hidden_size * s.controller_num_layers,
+                                                dtype=self.dtype)}
 
     def controller(self, inp, state):
         s, C = self.s, self.s.controller_hidden_size
@@ -106,9 +108,16 @@ class TorchRefNTM(object):
         out = torch.softmax(logit, dim=-1)
         return out, logit, M, w, read, ctrl
 
-    @torch.no_grad()
     def run(self, inputs, state=None):
-        """LoopNTMTracker: [B,T,D] -> (outputs, logits, final_state)."""
+        """LoopNTMTracker: [B,T,D] -> (outputs, logits, final_state).  Builds an autograd graph when
+        the parameters require gradients (used as the gradient oracle of the training path)."""
+        if not any(v.requires_grad for v in self.p.values()):
+            with torch.no_grad():
+                return self._run(inputs, state)
+        return self._run(inputs, state)
+
+    def _run(self, inputs, state=None):
+        inputs = inputs.to(self.dtype)
         B, T, _ = inputs.shape
         state = state or self.zero_state(B)
         xs = inputs.permute(1, 0, 2).contiguous()        # unstack_into_tensorarray (utility.py:61-91)
