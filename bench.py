@@ -35,7 +35,11 @@ WORKLOADS = {
     "c2_tracker": ("c2_tracker", "weak"),
     "c1_copy": ("c1_copy", "weak"),
     "c4_large": ("c4_large", "weak"),
+    # BASELINE configs[4]: forward + backward + NCCL gradient all-reduce + clip + RMSProp, 256 sequences
+    # per GPU, T = 32.  Synthetic frames of 8 rows (7 feature rows + delimiter) -> loss on 3 delimiter steps.
+    "c5_train": ("c5_train", "weak"),
 }
+TRAIN_FRAME = 8
 INIT_SCALE = 0.05       # direct_offset_output.py:42
 FEATURE_SCALE = 1.0     # synthetic conv4_3 features = max(0, N(0,1)) * FEATURE_SCALE
 
@@ -266,6 +270,14 @@ def main():
     trk = LoopNTMTracker(T, Odim, (-INIT_SCALE, INIT_SCALE), device=dev, **cell_kw)
     trk.cell.build(D, (-INIT_SCALE, INIT_SCALE))
     state = trk.cell.zero_state(B_local, (-INIT_SCALE, INIT_SCALE))
+    training = args.workload == "c5_train"
+    trainer = targets = None
+    if training:
+        from ntm_tracker_b200 import NTMTrainer
+        from ntm_tracker_b200.training import delimiter_steps
+        trainer = NTMTrainer(trk, frame=TRAIN_FRAME)
+        n_t = len(delimiter_steps(T, TRAIN_FRAME))
+        targets = (torch.rand(B_local, n_t, Odim, generator=torch.Generator().manual_seed(7 + rank)) - 0.5).to(dev)
     kind = "c1_copy" if cfg_name == "c1_copy" else "tracker"
     x_host = make_inputs_torch(kind, B_local, T, D, 1000 + rank).pin_memory()
     x_dev = x_host.to(dev)
@@ -286,8 +298,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def one_step():
-        trk(x_dev, state)
+    last_loss = [None]
+
+    def one_step(x=None):
+        if training:      # forward (with history) + backward + gradient all-reduce + clip + RMSProp
+            last_loss[0], _ = trainer.train_step(x_dev if x is None else x, targets)
+        else:
+            trk(x_dev if x is None else x, state)
 
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -324,17 +341,22 @@ def main():
     # ---------------- end-to-end: pinned host inputs in, host results out ------------------
     e2e = None
     if not args.no_e2e:
+        d2h = 4
         for _ in range(2):
-            trk(x_host, state)
+            one_step(x_host) if training else trk(x_host, state)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
-            out_h, log_h = trk(x_host, state)     # H2D copy, kernels, D2H of outputs + logits
+            if training:
+                one_step(x_host)                  # H2D copy of the frames, train step, D2H of the loss
+                float(last_loss[0])
+            else:
+                out_h, log_h = trk(x_host, state)     # H2D copy, kernels, D2H of outputs + logits
+                d2h = int(out_h.numel() + log_h.numel()) * 4
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
         e2e = {"value": B_total * T * args.steps / e2e_s, "unit": "seq-steps/s",
-               "h2d_bytes_per_step": int(input_bytes) * world,
-               "d2h_bytes_per_step": int(out_h.numel() + log_h.numel()) * 4 * world}
+               "h2d_bytes_per_step": int(input_bytes) * world, "d2h_bytes_per_step": d2h * world}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -351,6 +373,8 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     abytes = algorithmic_bytes_per_seqstep(kw)
+    if training:    # + HBM spill of the history (write forward, read backward), SURVEY.md s8d
+        abytes += 2 * (kw["mem_size"] * kw["mem_dim"] + (kw["read_head_size"] + kw["write_head_size"]) * kw["mem_size"]) * 4
     seq_avg_ms = sum(seq_ms) / len(seq_ms)
     achieved = abytes * B_local * T / (seq_avg_ms / 1e3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
@@ -385,7 +409,9 @@ def main():
                        parallelism="dp%d (sequences sharded, no per-step collective)" % world,
                        l2=l2_note, cluster_size=plan["cluster_size"],
                        sequences_resident=plan["sequences_resident"],
-                       smem_bytes_per_cta=plan["smem_bytes_per_cta"], **kw),
+                       smem_bytes_per_cta=plan["smem_bytes_per_cta"],
+                       mode=("train: fwd+bwd+allreduce+clip+RMSProp, frame=%d" % TRAIN_FRAME) if training else "forward",
+                       **kw),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "wall_s_timed_region": wall,

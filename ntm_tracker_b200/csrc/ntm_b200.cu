@@ -44,6 +44,11 @@
 using namespace ntm_b200;
 
 namespace {
+std::atomic<long long> g_launches{0};
+}
+void ntm_b200::count_launch() { g_launches++; }
+
+namespace {
 
 // ------------------------------------------------------------------ packing --
 __global__ void pack_ao_kernel(const float* __restrict__ aw, const float* __restrict__ ab,
@@ -71,8 +76,6 @@ std::atomic<int> g_profiling{0};
 thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
 thread_local bool g_ev_valid = false;
 thread_local int g_last_info[16] = {0};
-std::atomic<long long> g_launches{0};
-
 int set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
   return NTM_B200_ERR_CUDA;

@@ -77,6 +77,7 @@ struct KernelVariant {
   cudaError_t (*launch)(int R, int W, const KParams& p, int grid_ctas, int cluster_size, int smem_bytes,
                         bool cooperative, cudaStream_t stream);
 };
+void count_launch();   // bumps the library-wide kernel-launch counter (ntm_b200_launch_count)
 namespace k512 { const KernelVariant& variant(); }
 namespace k256 { const KernelVariant& variant(); }
 

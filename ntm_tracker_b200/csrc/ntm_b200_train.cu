@@ -542,5 +542,6 @@ extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_
     return NTM_B200_ERR_CUDA;
   }
   k<<<(unsigned)batch, NT, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
 }

@@ -314,6 +314,9 @@ CONFIGS = {
     "c3_sweep": (dict(output_dim=2, input_dim=514, mem_size=128, mem_dim=512, shift_range=1,
                       controller_hidden_size=200, controller_num_layers=1,
                       write_head_size=1, read_head_size=4), 4096, 64),
+    "c5_train": (dict(output_dim=2, input_dim=514, mem_size=128, mem_dim=512, shift_range=1,
+                      controller_hidden_size=200, controller_num_layers=1,
+                      write_head_size=1, read_head_size=4), 256, 32),
     "c4_large": (dict(output_dim=2, input_dim=514, mem_size=1024, mem_dim=256, shift_range=1,
                       controller_hidden_size=200, controller_num_layers=1,
                       write_head_size=1, read_head_size=4), 512, 128),
