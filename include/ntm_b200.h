@@ -175,6 +175,19 @@ int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* shape, int64_t batch
                                       const float* d_read, const float* d_w, float* dM,
                                       float* d_w_prev, float* d_raw_params, void* stream);
 
+/* The data formats either side of the path.
+ * serialize: conv features [B, L, F, Cch] + first-frame target map [B, F] -> tracker inputs
+ * [B, L*(F+1), Cch+2] with a delimiter row per frame (last row of the frame as in training,
+ * direct_offset_output.py:439-500; first row when delimiter_first != 0 as in the serve path,
+ * test_tracker.py:400-404), channel Cch = delimiter bit, channel Cch+1 = target (first F steps).
+ * gather: logits [B, L*(F+1), O] -> tanh(logits at each frame's delimiter row, first frame
+ * dropped) [B, L-1, O]  (direct_offset_output.py:581-593). */
+int32_t ntm_b200_serialize_tracker_inputs(const float* features, const float* target, float* inputs,
+                                          int64_t batch, int32_t frames, int32_t num_features,
+                                          int32_t channels, int32_t delimiter_first, void* stream);
+int32_t ntm_b200_gather_offsets(const float* logits, float* offsets, int64_t batch, int32_t frames,
+                                int32_t num_features, int32_t output_dim, void* stream);
+
 /* NTMCell.__call__ (ntm_cell.py:53-253): one step, inputs [B,D], logits/outputs
  * [B,O].  The serve path's unit of work (test_tracker.py:284-299). */
 int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weights,

@@ -65,6 +65,10 @@ SYMBOLS = {
                                                C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.POINTER(History), C.c_void_p, C.c_int64, C.c_void_p]),
     "ntm_b200_memory_backward_step": (C.c_int32, [C.POINTER(Shape), C.c_int64] + [C.c_void_p] * 9),
+    "ntm_b200_serialize_tracker_inputs": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ntm_b200_gather_offsets": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p]),
     "ntm_b200_step": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p, C.c_int64,
                                   C.c_void_p, C.POINTER(State), C.POINTER(State), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -354,3 +354,32 @@ def tracker_inputs(B: int, T: int, seed: int, scale: float = 1.0,
     first = t < min(frame - 1, T)
     x[:, first, feat + 1] = (rng.rand(B, int(first.sum())) < 0.1).astype(np.float32)
     return x
+
+
+# --------------------------------------------------------------------------- #
+# Data formats either side of the path
+# --------------------------------------------------------------------------- #
+
+
+def serialize_tracker_inputs(features, target, delimiter_first=False):
+    """direct_offset_output.py:439-500 (delimiter row last) / test_tracker.py:392-404 (first).
+    features [B,L,F,C], target [B,F] -> [B, L*(F+1), C+2]."""
+    features = np.asarray(features)
+    B, L, F, Cc = features.shape
+    padded = np.concatenate([features, np.zeros((B, L, F, 1), features.dtype)], 3)       # :463-464
+    delim = np.zeros((B, L, 1, Cc + 1), features.dtype)
+    delim[..., Cc] = 1.0                                                                  # :467-475
+    frames = np.concatenate([delim, padded] if delimiter_first else [padded, delim], 2)  # :478-479
+    frames = frames.reshape(B, L * (F + 1), Cc + 1)                                       # :481-486
+    tgt = np.concatenate([np.asarray(target, features.dtype),
+                          np.zeros((B, (L - 1) * (F + 1) + 1), features.dtype)], 1)       # :490-494
+    return np.concatenate([frames, tgt[..., None]], -1)                                   # :496-498
+
+
+def gather_offsets(output_logits, num_features):
+    """direct_offset_output.py:581-593: drop the first frame, take each frame's delimiter row, tanh."""
+    lg = np.asarray(output_logits)
+    B, T, Od = lg.shape
+    L = T // (num_features + 1)
+    g = lg[:, num_features + 1:, :].reshape(B, L - 1, num_features + 1, Od)[:, :, num_features, :]
+    return np.tanh(g)

@@ -1,0 +1,65 @@
+"""GPU: the input serialiser and the output gather (csrc/ntm_b200_io.cu) against the NumPy
+restatement of direct_offset_output.py:439-500 / :581-593 -- bit-exact for the copy, 1e-6 for tanh."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+from oracle import ntm_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,L,F,C,first", [(3, 4, 64, 512, False), (2, 3, 64, 512, True), (5, 2, 7, 9, False),
+                                           (1, 6, 3, 1, True)])
+def test_serialize_matches_reference_layout(B, L, F, C, first):
+    from ntm_tracker_b200.serialize import tracker_inputs
+    rng = np.random.RandomState(B * 100 + L)
+    feat = np.maximum(rng.standard_normal((B, L, F, C)), 0).astype(np.float32)
+    tgt = rng.rand(B, F).astype(np.float32)
+    got = tracker_inputs(torch.from_numpy(feat).cuda(), torch.from_numpy(tgt).cuda(), delimiter_first=first)
+    exp = O.serialize_tracker_inputs(feat, tgt, delimiter_first=first)
+    assert got.shape == exp.shape == (B, L * (F + 1), C + 2)
+    assert np.array_equal(got.cpu().numpy(), exp)
+    # structure: one delimiter bit per frame, target only within the first F steps
+    x = got.cpu().numpy()
+    assert x[:, :, C].sum() == B * L
+    assert np.abs(x[:, F:, C + 1]).sum() == 0
+
+
+@pytest.mark.parametrize("B,L,F,Od", [(4, 5, 64, 2), (2, 2, 3, 5)])
+def test_gather_offsets(B, L, F, Od):
+    from ntm_tracker_b200.serialize import gather_offsets
+    lg = np.random.RandomState(L).standard_normal((B, L * (F + 1), Od)).astype(np.float32)
+    got = gather_offsets(torch.from_numpy(lg).cuda(), F).cpu().numpy()
+    exp = O.gather_offsets(lg, F)
+    assert got.shape == (B, L - 1, Od)
+    assert np.abs(got - exp).max() <= 1e-6
+
+
+def test_serialized_inputs_drive_the_tracker():
+    """features -> serialiser -> LoopNTMTracker -> gather, end to end on the device, vs the oracle."""
+    from ntm_tracker_b200 import LoopNTMTracker
+    from ntm_tracker_b200.serialize import gather_offsets, tracker_inputs
+    B, L, F, C = 3, 3, 4, 6
+    s = O.NTMShape(output_dim=2, input_dim=C + 2, mem_size=16, mem_dim=8, controller_hidden_size=10,
+                   controller_num_layers=1, write_head_size=1, read_head_size=2)
+    params = O.init_params(s, 3, 0.05)
+    rng = np.random.RandomState(1)
+    feat = np.maximum(rng.standard_normal((B, L, F, C)), 0).astype(np.float32)
+    tgt = rng.rand(B, F).astype(np.float32)
+    x = tracker_inputs(torch.from_numpy(feat).cuda(), torch.from_numpy(tgt).cuda())
+    trk = LoopNTMTracker(L * (F + 1), 2, mem_size=16, mem_dim=8, controller_hidden_size=10,
+                         controller_num_layers=1, write_head_size=1, read_head_size=2)
+    trk.cell.load_reference_weights(params)
+    _, logits = trk(x)
+    off = gather_offsets(logits, F).cpu().numpy()
+    _, rl, _ = O.run_sequence(params, s, O.serialize_tracker_inputs(feat, tgt))
+    assert np.abs(off - O.gather_offsets(rl, F)).max() <= 1e-4
+
+
+def test_bad_shapes_raise():
+    from ntm_tracker_b200.serialize import gather_offsets, tracker_inputs
+    with pytest.raises(ValueError):
+        tracker_inputs(torch.zeros(2, 3, 4, 5).cuda(), torch.zeros(2, 3).cuda())
+    with pytest.raises(ValueError):
+        gather_offsets(torch.zeros(2, 10, 2).cuda(), 3)
