@@ -14,5 +14,6 @@ _cabi.load()   # no library -> RuntimeError here, never a silent fallback
 from .ntm_cell import NTMCell, random_uniform_initializer  # noqa: E402
 from .ntm_tracker_new import LoopNTMTracker  # noqa: E402
 from .training import NTMTrainer  # noqa: E402
+from .session import ResidentTracker  # noqa: E402
 
-__all__ = ["NTMCell", "LoopNTMTracker", "NTMTrainer", "random_uniform_initializer"]
+__all__ = ["NTMCell", "LoopNTMTracker", "NTMTrainer", "ResidentTracker", "random_uniform_initializer"]

@@ -63,3 +63,29 @@ def test_bad_shapes_raise():
         tracker_inputs(torch.zeros(2, 3, 4, 5).cuda(), torch.zeros(2, 3).cuda())
     with pytest.raises(ValueError):
         gather_offsets(torch.zeros(2, 10, 2).cuda(), 3)
+
+
+def test_resident_tracker_session_matches_stepwise_oracle():
+    """Serve path (test_tracker.py:284-299): three frames of F+1 cell steps each, state carried on
+    the device between frames, against the oracle stepping the same rows one at a time."""
+    from ntm_tracker_b200 import NTMCell, ResidentTracker
+    F, C = 5, 6
+    s = O.NTMShape(output_dim=2, input_dim=C + 2, mem_size=16, mem_dim=8, controller_hidden_size=10,
+                   controller_num_layers=1, write_head_size=1, read_head_size=2)
+    params = O.init_params(s, 4, 0.05)
+    cell = NTMCell(2, mem_size=16, mem_dim=8, controller_hidden_size=10, controller_num_layers=1,
+                   write_head_size=1, read_head_size=2)
+    cell.load_reference_weights(params)
+    sess = ResidentTracker(cell, num_features=F, batch_size=1).reset()
+    rng = np.random.RandomState(5)
+    state = O.zero_state(params, s, 1)
+    for frame in range(3):
+        feat = np.maximum(rng.standard_normal((1, F, C)), 0).astype(np.float32)
+        tgt = rng.rand(1, F).astype(np.float32) if frame == 0 else np.zeros((1, F), np.float32)
+        got = sess.track(torch.from_numpy(feat).cuda(), torch.from_numpy(tgt).cuda()).cpu().numpy()
+        rows = O.serialize_tracker_inputs(feat[:, None], tgt, delimiter_first=True)[0]
+        for r in rows:
+            _, lg, state, _ = O.cell_step(params, s, r[None], state)
+        assert np.abs(got - np.tanh(lg)).max() <= 1e-4
+    for k in ("M", "w", "read"):
+        assert np.abs(sess.state[k].cpu().numpy() - state[k]).max() <= 1e-4
