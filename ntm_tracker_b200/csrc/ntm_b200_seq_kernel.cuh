@@ -525,31 +525,35 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   mark_slot(prow, tmark, 10);
 
   // ---- pass 1: sim[h][n] = sum_d kc[h][d] * M[n][d] over this CTA's rows (ops.py:156) ----
+  // A warp takes a block of RB1 rows and walks the columns in float4 chunks (one per lane): the
+  // H key chunks it loads are reused by all RB1 rows, so the shared-memory traffic of the pass is
+  // (1 + H / RB1) x the memory itself.  The pass is shared-memory-bandwidth bound.
   {
-    int LPR = 32;                      // lanes cooperating on one block of RB rows
+    constexpr int RB1 = RB;            // 8-row blocks halve the key traffic but leave half the warps idle: measured slower
+    int LPR = 32;                      // lanes cooperating on one block of rows
     while (LPR > 1 && (LPR >> 1) >= MC) LPR >>= 1;
     const int GPW = 32 / LPR;
     const int sg = lane / LPR, lg = lane - sg * LPR;
-    const int nRB = (nrows + RB - 1) / RB;
+    const int nRB = (nrows + RB1 - 1) / RB1;
     const int iters = (nRB + NWARP * GPW - 1) / (NWARP * GPW);
     for (int it = 0; it < iters; ++it) {
       const int rb = (it * NWARP + warp) * GPW + sg;
       const bool active = rb < nRB;
-      float acc[RB][H];
+      float acc[RB1][H];
 #pragma unroll
-      for (int i = 0; i < RB; ++i)
+      for (int i = 0; i < RB1; ++i)
 #pragma unroll
         for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
-      int rows[RB];
+      int rows[RB1];
 #pragma unroll
-      for (int i = 0; i < RB; ++i) rows[i] = min(rb * RB + i, nrows - 1);
+      for (int i = 0; i < RB1; ++i) rows[i] = min(rb * RB1 + i, nrows - 1);
       if (active) {
         for (int c = lg; c < MC; c += LPR) {
           float4 k4[H];
 #pragma unroll
           for (int h = 0; h < H; ++h) k4[h] = *reinterpret_cast<const float4*>(kS + h * M4 + 4 * c);
 #pragma unroll
-          for (int i = 0; i < RB; ++i) {
+          for (int i = 0; i < RB1; ++i) {
             const float4 m4 = *reinterpret_cast<const float4*>(Ms + rows[i] * M4 + 4 * c);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
@@ -561,24 +565,54 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
           }
         }
       }
-      for (int o = LPR >> 1; o > 0; o >>= 1) {
+      if (LPR == 32 && RB * H <= 32) {
+        // transposing reduction, RB rows at a time: at offset o a lane keeps one half of its value
+        // list and receives the partner's sums of that half -- 31 shuffles instead of 5 per value;
+        // lane L ends up with the warp total of value L = i * H + h (fixed order, deterministic).
 #pragma unroll
-        for (int i = 0; i < RB; ++i)
+        for (int g = 0; g < RB1 / RB; ++g) {
+          float v[32];
 #pragma unroll
-          for (int h = 0; h < H; ++h) acc[i][h] += __shfl_xor_sync(0xffffffffu, acc[i][h], o);
-      }
-      if (active && lg == 0) {
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < RB; ++i) {
-          const int rl = rb * RB + i;
-          if (rl < nrows) {
+          for (int i = 0; i < RB; ++i)
 #pragma unroll
-            for (int h = 0; h < H; ++h) simL[h * p.NR + rl] = acc[i][h];
+            for (int h = 0; h < H; ++h) v[i * H + h] = acc[g * RB + i][h];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const float send = up ? v[j] : v[j + o];
+              const float keep = up ? v[j + o] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          const int vi = lane / H, vh = lane - vi * H;      // value index -> (row in group, head)
+          const int rl = rb * RB1 + g * RB + vi;
+          if (active && lane < RB * H && rl < nrows) simL[vh * p.NR + rl] = v[0];
+        }
+      } else {
+        for (int o = LPR >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int i = 0; i < RB1; ++i)
+#pragma unroll
+            for (int h = 0; h < H; ++h) acc[i][h] += __shfl_xor_sync(0xffffffffu, acc[i][h], o);
+        }
+        if (active && lg == 0) {
+#pragma unroll
+          for (int i = 0; i < RB1; ++i) {
+            const int rl = rb * RB1 + i;
+            if (rl < nrows) {
+#pragma unroll
+              for (int h = 0; h < H; ++h) simL[h * p.NR + rl] = acc[i][h];
+            }
           }
         }
       }
     }
   }
+  mark_slot(prow, tmark, 6);
   cluster.sync();
   // all-gather over DSMEM: every CTA pulls all slices (its own included) from the owners' simL
   // buffers into its private full-length copy; simL is not touched again before the next step's
@@ -906,7 +940,6 @@ __global__ void NTM_KERNEL_BOUNDS ntm_seq_kernel(const KParams p) {
       mark(5);
       if (active)
         phase_d<R, W>(p, cluster, smem, crank, gslot, bglob, t, row0, nrows, wcur, prow, tmark, act[0], partC);
-      mark(6);
       grid_sync(ctr, p.err, epoch, ncta);
       mark(7);
     }

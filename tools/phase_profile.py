@@ -46,8 +46,8 @@ lib.ntm_b200_last_kernel_ms(C.byref(a), C.byref(b))
 cyc = np.array(buf, dtype=np.int64).reshape(ncta, 16)
 waves = -(-B // info["sequences_resident"])
 steps = waves * T
-names = ["A gemm", "A barrier", "B lstm", "B barrier", "C gemm", "C barrier", "D addressing",
-         "D barrier", "prologue", "epilogue", "D.0 params+acts", "D.1 kc+pass1+csync",
+names = ["A gemm", "A barrier", "B lstm", "B barrier", "C gemm", "C barrier", "D.1a pass1 compute",
+         "D barrier", "prologue", "epilogue", "D.0b activations", "D.1b csync+gather",
          "D.2 addressing", "D.3 pass2+csync", "D.4 finalize", "D.0a param loads"]
 mhz = 1965.0
 res = {"workload": wl, "B": B, "T": T, "ncta": ncta, "waves": waves, "launch": info, "seq_kernel_ms": b.value,
