@@ -51,19 +51,14 @@ __device__ __forceinline__ float warp_max(float v) {
 // v + sum over K-slices ks (ascending: fixed summation order) of p[ks * stride], with the loads of
 // each group of four issued before any of them is consumed (L2 latency overlapped).
 __device__ __forceinline__ float sum_slabs(const float* p, size_t stride, int KS, float v) {
-  int ks = 0;
-  for (; ks + 4 <= KS; ks += 4) {
-    const float a = __ldcg(p + (size_t)ks * stride), b = __ldcg(p + (size_t)(ks + 1) * stride);
-    const float c = __ldcg(p + (size_t)(ks + 2) * stride), d = __ldcg(p + (size_t)(ks + 3) * stride);
-    v += a; v += b; v += c; v += d;
-  }
-  if (ks < KS) {
-    const float a = __ldcg(p + (size_t)ks * stride);
-    const float b = (ks + 1 < KS) ? __ldcg(p + (size_t)(ks + 1) * stride) : 0.0f;
-    const float c = (ks + 2 < KS) ? __ldcg(p + (size_t)(ks + 2) * stride) : 0.0f;
-    v += a;
-    if (ks + 1 < KS) v += b;
-    if (ks + 2 < KS) v += c;
+  constexpr int INFL = 24;                  // L2 loads in flight per round (one round for KS <= 24)
+  for (int ks = 0; ks < KS; ks += INFL) {
+    float a[INFL];
+#pragma unroll
+    for (int i = 0; i < INFL; ++i) a[i] = (ks + i < KS) ? __ldcg(p + (size_t)(ks + i) * stride) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < INFL; ++i)
+      if (ks + i < KS) v += a[i];
   }
   return v;
 }
@@ -340,8 +335,16 @@ __device__ __forceinline__ void lstm_phase(const KParams& p, int l, int Gcur, in
     const int q = ii & 3, bu = ii >> 2;
     const int b = bu / C, u = bu - b * C;
     const int col = q * C + u;
-    float v = (l == 0) ? __ldg(p.xw + ((size_t)(b0 + b) * p.T + t) * (size_t)(4 * C) + col)
-                       : __ldg(p.bA[l] + col);
+    float v;
+    if (l == 0) {
+      const float* xp = p.xw + ((size_t)(b0 + b) * p.T + t) * (size_t)(4 * C) + col;
+      v = __ldg(xp);
+      // the hoisted projection streams from HBM once: pull the next step's row into L2 now so that its
+      // ~1 us DRAM latency is off the next step's critical path
+      if (t + 1 < p.T && (col & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + 4 * C));
+    } else {
+      v = __ldg(p.bA[l] + col);
+    }
     v = sum_slabs(partA + (size_t)b * g.NCs + col, (size_t)g.Gpad * g.NCs, KS, v);
     const unsigned lane = threadIdx.x & 31u, gl = lane & ~3u;
     const float zi = __shfl_sync(0xffffffffu, v, gl + 0);
