@@ -28,8 +28,14 @@ constexpr int NT = NTM_NT;       // threads per CTA
 constexpr int NWARP = NT / 32;
 
 // ------------------------------------------------------------------ helpers --
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+// Activations on the SFU: exp via one ex2 (2 ulp) and an IEEE reciprocal instead of libm's expf /
+// tanhf / division sequences.  Absolute error <= ~1.2e-7 (the 1 - 2/(1+e^2x) form cancels for small
+// |x|, which costs relative, not absolute, accuracy) -- three orders below the 1e-4 parity budget.
+__device__ __forceinline__ float exp_f(float x) { return exp2f(x * 1.4426950408889634f); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + exp_f(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * __frcp_rn(1.0f + exp_f(2.0f * x)); }
+// softplus(x) = max(x, 0) + log(1 + e^-|x|): never overflows; one ex2 + one lg2 (abs error ~1e-7)
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.0f) + __logf(1.0f + exp_f(-fabsf(x))); }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -356,8 +362,8 @@ __device__ __forceinline__ void lstm_phase(const KParams& p, int l, int Gcur, in
     if (ok && q == 0) {
       float* cp = cst + ((size_t)b * p.L + l) * C + u;
       const float c_prev = __ldcg(cp);
-      const float c_new = c_prev * sigmoid_f(zf) + sigmoid_f(zi) * tanhf(zj);
-      const float h_new = tanhf(c_new) * sigmoid_f(zo);
+      const float c_new = c_prev * sigmoid_f(zf) + sigmoid_f(zi) * tanh_f(zj);
+      const float h_new = tanh_f(c_new) * sigmoid_f(zo);
       *cp = c_new;
       if (p.hC != nullptr) p.hC[(((size_t)(t + 1) * p.B + (b0 + b)) * p.L + l) * C + u] = c_new;
       if (p.hH != nullptr) p.hH[(((size_t)(t + 1) * p.B + (b0 + b)) * p.L + l) * C + u] = h_new;
@@ -470,7 +476,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
       for (int d = tid; d < M4; d += NT) {
         float kv = 0.0f;
         if (d < M) {
-          kv = tanhf(raw[h * M + d]);
+          kv = tanh_f(raw[h * M + d]);
           if (dbg) dbg[h * M + d] = kv;
         }
         kS[h * M4 + d] = kv * cn[d];
@@ -488,7 +494,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
         float ev = 0.0f, av = 0.0f;
         if (d < M) {
           ev = sigmoid_f(raw[offE + h * M + d]);
-          av = tanhf(raw[offA + h * M + d]);
+          av = tanh_f(raw[offA + h * M + d]);
           if (dbg) { dbg[offE + h * M + d] = ev; dbg[offA + h * M + d] = av; }
         }
         eS[h * M4 + d] = ev;
@@ -505,8 +511,9 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     float mx = raw[offS + tid * S];
     for (int i = 1; i < S; ++i) mx = fmaxf(mx, raw[offS + tid * S + i]);
     float sum = 0.0f;
-    for (int i = 0; i < S; ++i) { sp[i] = expf(raw[offS + tid * S + i] - mx); sum += sp[i]; }
-    for (int i = 0; i < S; ++i) sp[i] = sp[i] / sum;
+    for (int i = 0; i < S; ++i) { sp[i] = exp_f(raw[offS + tid * S + i] - mx); sum += sp[i]; }
+    const float rsum = __frcp_rn(sum);
+    for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
     if (dbg) {
       dbg[offBeta + tid] = bv; dbg[offG + tid] = gv; dbg[offGam + tid] = gm;
       for (int i = 0; i < S; ++i) dbg[offS + tid * S + i] = sp[i];
@@ -518,10 +525,11 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     float mx = lg[0];
     for (int i = 1; i < p.O; ++i) mx = fmaxf(mx, lg[i]);
     float sum = 0.0f;
-    for (int i = 0; i < p.O; ++i) sum += expf(lg[i] - mx);
+    for (int i = 0; i < p.O; ++i) sum += exp_f(lg[i] - mx);
+    const float rsum = __frcp_rn(sum);
     for (int i = 0; i < p.O; ++i) {
       p.logits[o + i] = lg[i];
-      if (p.outputs) p.outputs[o + i] = expf(lg[i] - mx) / sum;
+      if (p.outputs) p.outputs[o + i] = exp_f(lg[i] - mx) * rsum;
     }
   }
   __syncthreads();
@@ -673,7 +681,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
       float sum = 0.0f;
 #pragma unroll 2
       for (int n = n0; n < N; n += nstep) {
-        const float e = expf(sh[n] - mx);
+        const float e = exp_f(sh[n] - mx);
         sh[n] = e;
         sum += e;
       }
