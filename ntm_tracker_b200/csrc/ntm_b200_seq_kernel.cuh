@@ -469,37 +469,50 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   // scalar and is applied to the similarities later); per-head sum of squares via fixed-order
   // warp partials.  Pad lanes d >= M are written as zeros.
   {
+    // loads first, then the H independent activation chains, then the stores: the compiler cannot
+    // hoist shared-memory loads over stores that might alias, so the order is spelled out here
     float ss[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      ss[h] = 0.0f;
-      for (int d = tid; d < M4; d += NT) {
-        float kv = 0.0f;
-        if (d < M) {
-          kv = tanh_f(raw[h * M + d]);
-          if (dbg) dbg[h * M + d] = kv;
-        }
-        kS[h * M4 + d] = kv * cn[d];
-        ss[h] = fmaf(kv, kv, ss[h]);
+    for (int h = 0; h < H; ++h) ss[h] = 0.0f;
+    for (int d = tid; d < M4; d += NT) {
+      float rv[H], re[W], ra[W];
+      const bool in = d < M;
+#pragma unroll
+      for (int h = 0; h < H; ++h) rv[h] = in ? raw[h * M + d] : 0.0f;
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        re[h] = in ? raw[offE + h * M + d] : 0.0f;
+        ra[h] = in ? raw[offA + h * M + d] : 0.0f;
       }
-      ss[h] = warp_sum(ss[h]);
+      const float cnd = cn[d];
+#pragma unroll
+      for (int h = 0; h < H; ++h) rv[h] = in ? tanh_f(rv[h]) : 0.0f;
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        re[h] = in ? sigmoid_f(re[h]) : 0.0f;
+        ra[h] = in ? tanh_f(ra[h]) : 0.0f;
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        kS[h * M4 + d] = rv[h] * cnd;
+        ss[h] = fmaf(rv[h], rv[h], ss[h]);
+        if (dbg && in) dbg[h * M + d] = rv[h];
+      }
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        eS[h * M4 + d] = re[h];
+        aS[h * M4 + d] = ra[h];
+        if (dbg && in) { dbg[offE + h * M + d] = re[h]; dbg[offA + h * M + d] = ra[h]; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {      // H interleaved warp reductions
+#pragma unroll
+      for (int h = 0; h < H; ++h) ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], o);
     }
     if (lane == 0) {
 #pragma unroll
       for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
-    }
-#pragma unroll
-    for (int h = 0; h < W; ++h) {
-      for (int d = tid; d < M4; d += NT) {
-        float ev = 0.0f, av = 0.0f;
-        if (d < M) {
-          ev = sigmoid_f(raw[offE + h * M + d]);
-          av = tanh_f(raw[offA + h * M + d]);
-          if (dbg) { dbg[offE + h * M + d] = ev; dbg[offA + h * M + d] = av; }
-        }
-        eS[h * M4 + d] = ev;
-        aS[h * M4 + d] = av;
-      }
     }
   }
   if (tid < H) {   // per-head scalars: beta, g, gamma (ntm_cell.py:140,151,169), shift softmax (:161)
@@ -764,18 +777,27 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
           const int n = row0 + row;
           float4* mp = reinterpret_cast<float4*>(Ms + row * M4 + 4 * c);
           const float4 m = *mp;
-          float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int h = 0; h < W; ++h) {
-            const float ww = wnew[(R + h) * Npad + n];
-            E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
-            E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
-            A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
-            A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
-          }
           float4 mn;
-          mn.x = fmaf(m.x, E.x, A.x); mn.y = fmaf(m.y, E.y, A.y);
-          mn.z = fmaf(m.z, E.z, A.z); mn.w = fmaf(m.w, E.w, A.w);
+          if constexpr (W == 1) {
+            // one write head: M' = M (1 - w e) + w a = M + w (a - M e): two FMAs per element
+            const float ww = wnew[R * Npad + n];
+            mn.x = fmaf(ww, fmaf(-m.x, e4[0].x, a4[0].x), m.x);
+            mn.y = fmaf(ww, fmaf(-m.y, e4[0].y, a4[0].y), m.y);
+            mn.z = fmaf(ww, fmaf(-m.z, e4[0].z, a4[0].z), m.z);
+            mn.w = fmaf(ww, fmaf(-m.w, e4[0].w, a4[0].w), m.w);
+          } else {
+            float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+              const float ww = wnew[(R + h) * Npad + n];
+              E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
+              E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
+              A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
+              A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
+            }
+            mn.x = fmaf(m.x, E.x, A.x); mn.y = fmaf(m.y, E.y, A.y);
+            mn.z = fmaf(m.z, E.z, A.z); mn.w = fmaf(m.w, E.w, A.w);
+          }
           const float4 mu = p.write_first ? mn : m;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
