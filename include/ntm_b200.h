@@ -188,6 +188,17 @@ int32_t ntm_b200_serialize_tracker_inputs(const float* features, const float* ta
 int32_t ntm_b200_gather_offsets(const float* logits, float* offsets, int64_t batch, int32_t frames,
                                 int32_t num_features, int32_t output_dim, void* stream);
 
+/* Backward of one BasicLSTMCell layer at one timestep for `batch` sequences (elementwise part; the
+ * two GEMMs around it stay with the caller).  dh = dh_a + dh_b (dh_b may be NULL) is the gradient
+ * w.r.t. the layer's new hidden state, dc [B,C] carries the cell-state gradient in and out, z holds
+ * the recorded gate pre-activations i|j|f|o of sequence b at z + b*z_stride, c_prev / c_new the cell
+ * state before / after the step at + b*c_stride, dz receives the pre-activation gradients at
+ * dz + b*dz_stride (4*C floats). */
+int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, const float* dh_a, const float* dh_b,
+                                    const float* z, int64_t z_stride, const float* c_prev,
+                                    const float* c_new, int64_t c_stride, float* dc, float* dz,
+                                    int64_t dz_stride, void* stream);
+
 /* NTMCell.__call__ (ntm_cell.py:53-253): one step, inputs [B,D], logits/outputs
  * [B,O].  The serve path's unit of work (test_tracker.py:284-299). */
 int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weights,

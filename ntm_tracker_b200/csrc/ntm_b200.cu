@@ -169,7 +169,8 @@ int make_host_plan(const ntm_b200_shape* s, int nsm, int smem_optin, HostPlan* h
   // each run the same ~35 us step (C2: 35.0 us vs 32.3 us single team) -- hence off by default.
   const int half_budget = std::min(smem_optin, B200_SMEM_SM / 2 - 1024 - 2048);   // slack for allocation granularity
   bool ok = false;
-  if (getenv("NTM_B200_DUAL_TEAM") != nullptr) {
+  // (tensor path only: with the SIMT GEMMs the two-team build is known to time out at 35 sequences per team)
+  if (getenv("NTM_B200_DUAL_TEAM") != nullptr && getenv("NTM_B200_DISABLE_TC") == nullptr) {
     for (int CS = 1; CS <= 8 && !ok; CS *= 2) {
       if (layout_for(s, CS, 8, half_budget, hp)) {
         ok = true;

@@ -479,6 +479,30 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
   for (int i = q.P + tid; i < q.PO4; i += NT) draw[i] = 0.0f;   // logit slots belong to the caller
 }
 
+// LSTM cell backward for one layer and one timestep, all sequences: elementwise over [B, C].
+// BasicLSTMCell forward (TF 1.0/1.1): c' = c*sig(f) + sig(i)*tanh(j); h' = tanh(c')*sig(o).
+__global__ void lstm_backward_kernel(int B, int C, const float* __restrict__ dh_a, const float* __restrict__ dh_b,
+                                     const float* __restrict__ z, long long z_stride,
+                                     const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                     long long c_stride, float* __restrict__ dc, float* __restrict__ dz,
+                                     long long dz_stride) {
+  const int total = B * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / C, u = i - b * C;
+    const float* zb = z + (size_t)b * z_stride;
+    const float gi = sigmoid_f(zb[u]), gj = tanhf(zb[C + u]), gf = sigmoid_f(zb[2 * C + u]), go = sigmoid_f(zb[3 * C + u]);
+    const float cp = c_prev[(size_t)b * c_stride + u], tc = tanhf(c_new[(size_t)b * c_stride + u]);
+    const float dh = dh_a[i] + (dh_b ? dh_b[i] : 0.0f);
+    const float dct = dc[i] + dh * go * (1.0f - tc * tc);
+    float* dzb = dz + (size_t)b * dz_stride;
+    dzb[u] = dct * gj * gi * (1.0f - gi);
+    dzb[C + u] = dct * gi * (1.0f - gj * gj);
+    dzb[2 * C + u] = dct * cp * gf * (1.0f - gf);
+    dzb[3 * C + u] = dh * tc * go * (1.0f - go);
+    dc[i] = dct * gf;
+  }
+}
+
 typedef void (*BwdKernel)(const BwdParams);
 #define NTM_BK(R, W) mem_backward_kernel<R, W>
 static BwdKernel select_bwd(int R, int W) {
@@ -543,5 +567,25 @@ extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_
   }
   k<<<(unsigned)batch, NT, smem, static_cast<cudaStream_t>(stream)>>>(q);
   count_launch();
+  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+}
+
+extern "C" int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, const float* dh_a, const float* dh_b,
+                                               const float* z, int64_t z_stride, const float* c_prev,
+                                               const float* c_new, int64_t c_stride, float* dc, float* dz,
+                                               int64_t dz_stride, void* stream) {
+  if (!dh_a || !z || !c_prev || !c_new || !dc || !dz) return NTM_B200_ERR_NULL_POINTER;
+  if (batch < 1 || hidden < 1 || batch * (int64_t)hidden > (1ll << 30)) return NTM_B200_ERR_BAD_SHAPE;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      major != 10) {
+    cudaGetLastError();
+    return NTM_B200_ERR_NO_DEVICE;
+  }
+  const int total = (int)(batch * hidden);
+  const int blocks = std::min((total + 255) / 256, ntm_b200::B200_SMS * 8);
+  ntm_b200::train::lstm_backward_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (int)batch, hidden, dh_a, dh_b, z, z_stride, c_prev, c_new, c_stride, dc, dz, dz_stride);
+  ntm_b200::count_launch();
   return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
 }

@@ -10,8 +10,9 @@ Here:
                 (``ntm_b200_forward_seq_train``);
   * backward -- reverse-time loop; the memory / addressing part of every step is ONE hand-written
                 kernel (``ntm_b200_memory_backward_step``, csrc/ntm_b200_train.cu); the dense
-                projections' data- and weight-gradients are plain GEMMs (``torch.matmul`` = cuBLAS)
-                and the LSTM gate algebra is elementwise torch;
+                projections' data- and weight-gradients are plain GEMMs (``torch.matmul`` = cuBLAS);
+  * the LSTM gate algebra's backward is one elementwise kernel per layer and step
+                (``ntm_b200_lstm_backward_step``);
   * multi-GPU -- sequences are sharded over ranks (no collective in forward or backward); the ONE
                 collective of the path is an all-reduce (sum) of the flat gradient over NCCL, followed
                 by the same clip + RMSProp on every rank, so the replicas stay identical.
@@ -98,22 +99,16 @@ class NTMTrainer(object):
                 dw_prev.data_ptr(), draw.data_ptr(), stream), "memory_backward_step")
             dw, dw_prev = dw_prev, dw
             draw[:, P:P + O] = dlogits[:, t]
-            d_in = torch.matmul(draw, Wao.t())                                  # dL/dh_top via both projections
+            d_in = torch.matmul(draw, Wao.t()).contiguous()                     # dL/dh_top via both projections
             for l in range(L - 1, -1, -1):
-                dh_l = dh[l] + d_in
-                z = hist["z"][t, :, l]
-                gi_, gj, gf, go = torch.sigmoid(z[:, 0]), torch.tanh(z[:, 1]), torch.sigmoid(z[:, 2]), torch.sigmoid(z[:, 3])
-                c_prev, tc = hist["c"][t, :, l], torch.tanh(hist["c"][t + 1, :, l])
-                dc_tot = dc[l] + dh_l * go * (1.0 - tc * tc)
-                dz = DZ[t, :, l]
-                dz[:, 0 * Cc:1 * Cc] = dc_tot * gj * gi_ * (1.0 - gi_)
-                dz[:, 1 * Cc:2 * Cc] = dc_tot * gi_ * (1.0 - gj * gj)
-                dz[:, 2 * Cc:3 * Cc] = dc_tot * c_prev * gf * (1.0 - gf)
-                dz[:, 3 * Cc:4 * Cc] = dh_l * tc * go * (1.0 - go)
-                dc[l] = dc_tot * gf
-                d_cat = torch.matmul(dz, Wl[l].t())                             # [B, in_l + C]
-                dh[l] = d_cat[:, -Cc:]
-                d_in = d_cat[:, :-Cc]
+                # elementwise LSTM backward (one kernel): dz -> DZ[t, :, l], dc[l] updated in place
+                _cabi.check(lib.ntm_b200_lstm_backward_step(
+                    B, Cc, dh[l].data_ptr(), d_in.data_ptr(), hist["z"][t, :, l].data_ptr(), L * 4 * Cc,
+                    hist["c"][t, :, l].data_ptr(), hist["c"][t + 1, :, l].data_ptr(), L * Cc,
+                    dc[l].data_ptr(), DZ[t, :, l].data_ptr(), L * 4 * Cc, stream), "lstm_backward_step")
+                d_cat = torch.matmul(DZ[t, :, l], Wl[l].t())                    # [B, in_l + C]
+                dh[l] = d_cat[:, -Cc:].contiguous()
+                d_in = d_cat[:, :-Cc].contiguous() if l > 0 else d_cat[:, :-Cc]
             dread = d_in[:, D:].reshape(B, R, M).contiguous()
 
         # ---- weight gradients: one GEMM per variable over all (t, b) ----

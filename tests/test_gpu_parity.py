@@ -315,3 +315,42 @@ def test_degenerate_state_no_nan():
         assert torch.isfinite(v).all()
     ro, rl, rs, _ = O.cell_step(params, s, np.zeros((2, 3)), {k: to_np(v) for k, v in st.items()})
     assert maxerr(to_np(st2["w"]), rs["w"]) <= TOL
+
+
+def test_cabi_error_paths_on_device():
+    """C-ABI misuse is reported by status code, never by a crash: workspace too small, null
+    pointers, bad batch (the reference raises ValueError from _linear, ntm_cell.py:334-347)."""
+    import ctypes as C
+    from ntm_tracker_b200 import NTMCell, _cabi
+    lib = _cabi.load()
+    cell = NTMCell(2, mem_size=16, mem_dim=8, controller_hidden_size=10, controller_num_layers=1,
+                   write_head_size=1, read_head_size=2)
+    cell.build(5, (-0.05, 0.05))
+    x = torch.zeros(3, 4, 5).cuda()
+    st = cell.zero_state(3)
+    with pytest.raises(ValueError):
+        cell._run(x, {**st, "M": st["M"][:, :8]}, 4)              # wrong state shape
+    with pytest.raises(ValueError):
+        cell(torch.zeros(3, 5, 1).cuda(), st)                        # cell step wants 2-D inputs
+    with pytest.raises(ValueError):
+        cell(torch.zeros(3, 6).cuda(), st)                           # wrong input width
+    shp = cell._shape_struct(5)
+    plan = _cabi.Plan()
+    assert lib.ntm_b200_query(C.byref(shp), 3, 4, C.byref(plan)) == 0
+    wts = cell._weights_struct()
+    packed = torch.empty(int(plan.packed_bytes), dtype=torch.uint8, device="cuda")
+    assert lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), packed.data_ptr(), 8, None) == 6      # too small
+    assert lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), packed.data_ptr(), packed.numel(), None) == 0
+    inner = {"M": 16 * 8, "w": 3 * 16, "read": 2 * 8, "controller_state": 20}
+    new = {k: torch.empty_like(v.contiguous()) for k, v in st.items()}
+    sin, k1 = NTMCell._state_struct(st, inner)
+    sout, k2 = NTMCell._state_struct(new, inner)
+    logits = torch.empty(3, 4, 2, device="cuda")
+    ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device="cuda")
+    args = lambda wsz, inp: (C.byref(shp), C.byref(wts), packed.data_ptr(), 3, 4, inp, C.byref(sin), C.byref(sout),
+                             logits.data_ptr(), None, None, ws.data_ptr(), wsz, None)
+    assert lib.ntm_b200_forward_seq(*args(1024, x.data_ptr())) == 6                                     # workspace too small
+    assert lib.ntm_b200_forward_seq(*args(ws.numel(), None)) == 3                                       # null inputs
+    assert lib.ntm_b200_forward_seq(*args(ws.numel(), x.data_ptr())) == 0
+    assert lib.ntm_b200_finish(ws.data_ptr(), None) == 0
+    assert torch.isfinite(logits).all()
