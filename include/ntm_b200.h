@@ -218,6 +218,11 @@ int32_t ntm_b200_finish(void* workspace, void* stream);
  * synchronised ntm_b200_last_kernel_ms returns their device durations. */
 int32_t ntm_b200_set_profiling(int32_t enable);
 int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms);
+/* Streaming mode (large batches): with profiling enabled, device time of the last
+ * call summed over its timesteps, out4 = {controller GEMM + LSTM gates, head-parameter GEMM, fused
+ * addressing/memory kernel, state initialisation} in ms; *steps = number of timesteps (0 when the last
+ * call on this thread did not run in streaming mode). */
+int32_t ntm_b200_last_stream_ms(float* out4, int32_t* steps);
 /* With profiling enabled the persistent kernel also accumulates, per CTA, SM-clock
  * cycles spent in each phase of the timestep (16 int64 slots per CTA: 0/2/4/6 =
  * phases A/B/C/D compute, 1/3/5/7 = the device-wide barrier after each, 8 =
@@ -228,7 +233,8 @@ int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_c
 /* Geometry of this thread's last ntm_b200_forward_seq launch, 16 ints: {tensor path used (0/1),
  * resident sequences, CTAs, cluster size, K-slices and K-slice width of the layer-0 controller
  * GEMM, K-slices and K-slice width of the head-parameter GEMM, teams, threads per CTA, CTAs per
- * SM, shared-memory bytes per CTA, 0...}. */
+ * SM, shared-memory bytes per CTA, x-projection on the tensor path (0/1), execution mode (0 = persistent
+ * shared-memory-resident kernel, 1 = streaming), 0...}. */
 int32_t ntm_b200_last_launch_info(int32_t* out16);
 
 /* Number of kernel launches the library has issued in this process (for the

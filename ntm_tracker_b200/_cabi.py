@@ -78,6 +78,7 @@ SYMBOLS = {
     "ntm_b200_finish": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "ntm_b200_set_profiling": (C.c_int32, [C.c_int32]),
     "ntm_b200_last_kernel_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "ntm_b200_last_stream_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ntm_b200_phase_cycles": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "ntm_b200_last_launch_info": (C.c_int32, [C.POINTER(C.c_int32)]),
     "ntm_b200_launch_count": (C.c_int64, []),
@@ -122,5 +123,14 @@ def last_launch_info():
     buf = (C.c_int32 * 16)()
     check(load().ntm_b200_last_launch_info(buf), "last_launch_info")
     keys = ("tensor_path", "sequences_resident", "ctas", "cluster_size", "ks_ctrl", "kw_ctrl", "ks_heads",
-            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta", "xproj_tensor_path")
+            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta", "xproj_tensor_path", "streaming")
     return dict(zip(keys, list(buf)))
+
+
+def last_stream_ms():
+    """Streaming mode, profiling enabled: device ms of the last call summed over its timesteps
+    ({'controller', 'head_params', 'memory', 'init', 'steps'}); steps == 0 if it was not a streaming call."""
+    buf = (C.c_float * 4)()
+    steps = C.c_int32(0)
+    check(load().ntm_b200_last_stream_ms(buf, C.byref(steps)), "last_stream_ms")
+    return {"controller": buf[0], "head_params": buf[1], "memory": buf[2], "init": buf[3], "steps": steps.value}

@@ -40,6 +40,7 @@
 #include "ntm_b200_params.h"
 #include "ntm_b200_xproj.cuh"
 #include "ntm_b200_xproj_tc.cuh"
+#include "ntm_b200_stream.h"
 
 using namespace ntm_b200;
 
@@ -47,6 +48,19 @@ namespace {
 std::atomic<long long> g_launches{0};
 }
 void ntm_b200::count_launch() { g_launches++; }
+
+namespace {
+thread_local char g_cuda_err[256] = "";
+}
+int ntm_b200::set_cuda_error_ext(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return NTM_B200_ERR_CUDA;
+}
+int ntm_b200::gemm_tc(const float* x, int ldx, const float* w, int ldw, const float* bias, float* out, int ldo,
+                      long long slab, long long rows, int K, int ncols, int kslices, int nsm, cudaStream_t stream) {
+  return launch_gemm_tc(x, ldx, w, ldw, bias, out, ldo, slab, rows, K, ncols, kslices, nsm, stream);
+}
+int ntm_b200::gemm_tc_slices(int K) { return gemm_tc_kslices(K); }
 
 namespace {
 
@@ -71,15 +85,11 @@ __global__ void pack_ao_kernel(const float* __restrict__ aw, const float* __rest
 }
 
 // --------------------------------------------------------------- host side --
-thread_local char g_cuda_err[256] = "";
 std::atomic<int> g_profiling{0};
 thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
 thread_local bool g_ev_valid = false;
 thread_local int g_last_info[16] = {0};
-int set_cuda_error(cudaError_t e, const char* where) {
-  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
-  return NTM_B200_ERR_CUDA;
-}
+int set_cuda_error(cudaError_t e, const char* where) { return set_cuda_error_ext(e, where); }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
@@ -334,6 +344,21 @@ int check_state(const ntm_b200_state* st) {
   return NTM_B200_OK;
 }
 
+// Execution mode for a call: 0 = persistent shared-memory-resident kernel, 1 = streaming (lockstep over
+// the whole shard, memory streamed from HBM).  NTM_B200_MODE=resident|stream overrides the choice.
+int choose_mode(const ntm_b200_shape* s, const HostPlan& hp, long long B, bool debug_taps, int nsm) {
+  if (debug_taps || !stream_supported(s, nsm)) return 0;
+  const char* m = getenv("NTM_B200_MODE");
+  if (m != nullptr && m[0] == 'r') return 0;
+  if (m != nullptr && m[0] == 's') return 1;
+  // resident: ceil(B / G) waves of ~30 us steps; streaming pays ~4 launches + GEMM weight loads per step
+  // but its step time grows only with the HBM traffic.  Measured crossover (profiles/): a few waves.
+  long long thr = 3ll * hp.Gteam_max * hp.max_teams;
+  const char* t = getenv("NTM_B200_STREAM_MIN_BATCH");
+  if (t != nullptr) thr = atoll(t);
+  return B > thr ? 1 : 0;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------- C ABI --
@@ -379,7 +404,9 @@ int32_t ntm_b200_query(const ntm_b200_shape* shape, int64_t batch, int64_t steps
   plan_out->ctas_per_sm = hp.ctas_per_sm;
   plan_out->teams = teams;
   plan_out->smem_bytes_per_cta = 4ll * hp.smem_floats;
-  plan_out->workspace_bytes = ws.total;
+  StreamWorkspace sws{};
+  stream_layout(shape, batch, steps, &sws);
+  plan_out->workspace_bytes = std::max(ws.total, sws.total + 1024);
   plan_out->packed_bytes = hp.packed_bytes;
   plan_out->debug_floats_per_sequence = hp.debug_floats;
   return NTM_B200_OK;
@@ -440,10 +467,14 @@ int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_w
     if (!weights->lstm_w[l] || !weights->lstm_b[l]) return NTM_B200_ERR_NULL_POINTER;
   Workspace ws{};
   layout_workspace(shape, hp, batch, steps, &ws);
-  if (workspace_bytes < ws.total) return NTM_B200_ERR_WORKSPACE;
+  StreamWorkspace sws{};
+  stream_layout(shape, batch, steps, &sws);
+  const int mode = choose_mode(shape, hp, batch, debug_taps != nullptr, di.nsm);
+  if (workspace_bytes < (mode ? sws.total + 1024 : ws.total)) return NTM_B200_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char* wsb = static_cast<char*>(workspace);
   cudaError_t e;
+  g_last_info[13] = mode;
 
   const KernelVariant& kv = variant_of(hp);
   const int R = shape->read_head_size, W = shape->write_head_size;
@@ -468,7 +499,9 @@ int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_w
     cudaEventRecord(g_ev[0], stream);
   }
   // hoisted x-projection: xw[b,t,:] = x[b,t,:] @ W_lstm0[0:D,:] + b_lstm0
-  float* xw = reinterpret_cast<float*>(wsb + ws.off_xw);
+  // (streaming mode: the first 1 KiB of the workspace stays the error-flag block ntm_b200_finish reads)
+  char* swsb = wsb + 1024;
+  float* xw = mode ? reinterpret_cast<float*>(swsb + sws.off_xw) : reinterpret_cast<float*>(wsb + ws.off_xw);
   // tensor-core kernel (tcgen05, weight tile resident in TMEM + SMEM); fp32 SIMT kernel for shapes it
   // does not cover or when NTM_B200_DISABLE_TC is set
   st = -1;
@@ -481,6 +514,24 @@ int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_w
                                 (long long)batch * steps, shape->input_dim, 4 * C, stream);
   g_launches++;
   if (st) return set_cuda_error(cudaGetLastError(), "xproj");
+
+  if (mode == 1) {
+    e = cudaMemsetAsync(wsb, 0, 1024, stream);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync");
+    if (prof) cudaEventRecord(g_ev[1], stream);
+    const float* wCp = static_cast<const float*>(packed);
+    st = stream_forward(shape, weights, wCp, wCp + (size_t)C * hp.PO4, batch, steps, xw, state_in, state_out,
+                        logits, outputs, history, swsb, sws, di.nsm, stream, prof);
+    if (st) return st;
+    if (prof) {
+      cudaEventRecord(g_ev[2], stream);
+      g_ev_valid = true;
+    }
+    g_last_info[0] = 1; g_last_info[1] = (int)batch; g_last_info[2] = (int)batch; g_last_info[3] = 1;
+    g_last_info[4] = sws.ksA[0]; g_last_info[6] = sws.ksC; g_last_info[8] = 1;
+    g_last_info[9] = 256; g_last_info[10] = stream_mem_occupancy();
+    return NTM_B200_OK;
+  }
 
   KParams p{};
   p.D = shape->input_dim; p.O = shape->output_dim; p.N = shape->mem_size; p.M = shape->mem_dim;
@@ -575,6 +626,12 @@ int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms) {
   if (e != cudaSuccess) return set_cuda_error(e, "cudaEventElapsedTime");
   e = cudaEventElapsedTime(seq_kernel_ms, g_ev[1], g_ev[2]);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaEventElapsedTime");
+  return NTM_B200_OK;
+}
+
+int32_t ntm_b200_last_stream_ms(float* out4, int32_t* steps) {
+  if (!out4 || !steps) return NTM_B200_ERR_NULL_POINTER;
+  *steps = stream_last_ms(out4);
   return NTM_B200_OK;
 }
 

@@ -1,0 +1,1295 @@
+// ntm_b200_stream.cu -- streaming (throughput) mode of the NTM sequence path for batches far larger
+// than what fits the SMs' shared memory.
+//
+// What it replaces (paths relative to the reference root), per timestep and for ALL sequences of the
+// shard in lockstep:
+//   controller projection + BasicLSTMCell ... ntm_cell.py:101-105     -> gemm_tc (tcgen05) + lstm_stream_kernel
+//   _linear head parameters + logits ........ ntm_cell.py:113-130,220 -> gemm_tc (tcgen05)
+//   activations, batched_smooth_cosine_similarity, content focus, gate, batched_circular_convolution,
+//   sharpening, erase/add write, read ....... ntm_cell.py:133-215, ops.py:135-242 -> mem_step_kernel
+//
+// mem_step_kernel is the HBM-bound kernel of this mode: one CTA per sequence-step.  Pass 1 streams the
+// sequence's N x M memory from HBM (similarities), the addressing runs in shared memory, pass 2 streams
+// the memory again -- out of L2, where pass 1 just put it -- and writes M' back: one HBM read and one
+// HBM write of M per sequence-step instead of the three passes of the algorithmic count.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "ntm_b200_stream.h"
+
+namespace ntm_b200 {
+namespace {
+
+__device__ __forceinline__ float exp_f(float x) { return exp2f(x * 1.4426950408889634f); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + exp_f(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * __frcp_rn(1.0f + exp_f(2.0f * x)); }
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.0f) + __logf(1.0f + exp_f(-fabsf(x))); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+inline long long align_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
+
+constexpr int RB = 4;        // rows per transposing reduction group in pass 1
+constexpr int RB1 = 8;       // rows a warp streams at once in pass 1 (two groups)
+constexpr int U2 = 8;        // rows a thread keeps in flight in pass 2
+
+struct MemArgs {
+  int N, M, M4, MC, Npad, S, shift0, P, PO4, O, write_first, T, t;
+  int nslab; long long slab;                 // raw[q] = bias[q] + sum_s mc[s*slab + b*PO4 + q]
+  const float* mc; const float* bias;
+  const float* Min; long long sMin;          // memory entering the step [B][N][M]
+  float* Mout; long long sMout;              // memory leaving it (may be the same buffer)
+  const float* w_in; long long sw_in;        // weightings entering the step [B][H][N]
+  float* w_out; long long sw_out;
+  float* cn;                                 // [B][M4] inverse column norms, in: of Min, out: of Mout
+  float* act_read; long long s_act;          // read vectors -> next step's controller input rows
+  float* read_out; long long s_read;         // state / history copy of the read vectors (may be null)
+  float* logits; float* outputs;             // [B][T][O]
+  int oK, oE, oA, oSim, oWg, oWn, oSm, oX;   // shared-memory carve-up (floats)
+  int WPC;                                   // warps sharing one 8-chunk column group in pass 2
+  // TMA-ring kernel: stages of RPS memory rows, NS stages, NCH chunks per pass
+  int RPS, NS, NCH, RP;                      // RP: row phases of pass 2 (threads = RP * MC)
+  int oWp, oRaw, oBar, oRing;                // w_prev copy, raw parameter row, mbarriers, ring (floats)
+  int l2_hints;
+};
+
+// ------------------------------------------------------------------------------------------------
+// One CTA = one sequence, one timestep.
+template <int R, int W, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
+  constexpr int H = R + W, NWARP = NT / 32;
+  extern __shared__ float4 mem_smem4[];
+  float* smem = reinterpret_cast<float*>(mem_smem4);
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, M = a.M, M4 = a.M4, MC = a.MC, Npad = a.Npad, S = a.S;
+  float* kS = smem + a.oK;      // [H][M4]  tanh(k) * cn
+  float* eS = smem + a.oE;      // [W][M4]
+  float* aS = smem + a.oA;      // [W][M4]
+  float* simS = smem + a.oSim;  // [H][Npad]
+  float* wg = smem + a.oWg;     // [H][Npad]
+  float* wnew = smem + a.oWn;   // [H][Npad]
+  float* sm = smem + a.oSm;     // beta[H] g[H] gamma[H] pad[H] sw[H][SMAX] sPart[NWARP][H] sRed[H][3][WPH]
+  float* xch = smem + a.oX;     // [WPC][R+1][M4]
+  float* sBeta = sm, *sG = sm + H, *sGam = sm + 2 * H, *sSw = sm + 4 * H;
+  float* sPart = sm + 4 * H + H * SMAX;
+  float* sRed = sPart + NWARP * H;
+  const float* Mi = a.Min + (size_t)b * a.sMin;
+  float* Mo = a.Mout + (size_t)b * a.sMout;
+  float* cnb = a.cn + (size_t)b * M4;
+
+  const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
+            offE = offGam + H, offA = offE + M * W;
+  const float* mcb = a.mc + (size_t)b * a.PO4;
+  auto rawv = [&](int q) -> float {
+    float v = a.bias != nullptr ? __ldg(a.bias + q) : 0.0f;
+    for (int s = 0; s < a.nslab; ++s) v += __ldcg(mcb + (size_t)s * a.slab + q);
+    return v;
+  };
+
+  // ---- activations (ntm_cell.py:133-196).  kS[h][d] = tanh(k) * cn[d]: the key's own 1/|k| is a
+  //      per-head scalar applied to the similarities later; pad lanes d >= M are zeros ----
+  {
+    float ss[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) ss[h] = 0.0f;
+    for (int d = tid; d < M4; d += NT) {
+      float rv[H], re[W], ra[W];
+      const bool in = d < M;
+#pragma unroll
+      for (int h = 0; h < H; ++h) rv[h] = in ? rawv(h * M + d) : 0.0f;
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        re[h] = in ? rawv(offE + h * M + d) : 0.0f;
+        ra[h] = in ? rawv(offA + h * M + d) : 0.0f;
+      }
+      const float cnd = in ? __ldcg(cnb + d) : 0.0f;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        rv[h] = in ? tanh_f(rv[h]) : 0.0f;
+        kS[h * M4 + d] = rv[h] * cnd;
+        ss[h] = fmaf(rv[h], rv[h], ss[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        eS[h * M4 + d] = in ? sigmoid_f(re[h]) : 0.0f;
+        aS[h * M4 + d] = in ? tanh_f(ra[h]) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
+    }
+  }
+  if (tid < H) {   // per-head scalars: beta, g, gamma (ntm_cell.py:140,151,169), shift softmax (:161)
+    sBeta[tid] = softplus_f(rawv(offBeta + tid));
+    sG[tid] = sigmoid_f(rawv(offG + tid));
+    sGam[tid] = 1.0f + softplus_f(rawv(offGam + tid));
+    float* sp = sSw + tid * SMAX;
+    float mx = -INFINITY;
+    for (int i = 0; i < S; ++i) { sp[i] = rawv(offS + tid * S + i); mx = fmaxf(mx, sp[i]); }
+    float sum = 0.0f;
+    for (int i = 0; i < S; ++i) { sp[i] = exp_f(sp[i] - mx); sum += sp[i]; }
+    const float rsum = __frcp_rn(sum);
+    for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
+  }
+  if (tid == NT - 1) {   // output projection + softmax (ntm_cell.py:220-221)
+    const size_t o = ((size_t)b * a.T + a.t) * a.O;
+    float mx = -INFINITY;
+    for (int i = 0; i < a.O; ++i) mx = fmaxf(mx, rawv(a.P + i));
+    float sum = 0.0f;
+    for (int i = 0; i < a.O; ++i) sum += exp_f(rawv(a.P + i) - mx);
+    const float rsum = __frcp_rn(sum);
+    for (int i = 0; i < a.O; ++i) {
+      const float lg = rawv(a.P + i);
+      a.logits[o + i] = lg;
+      if (a.outputs) a.outputs[o + i] = exp_f(lg - mx) * rsum;
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 1 (HBM): sim[h][n] = sum_d kS[h][d] * M[n][d]  (ops.py:156).  A warp streams RB1 rows at
+  //      once (RB1 independent 16-byte loads per lane in flight); the H key chunks it reads from shared
+  //      memory are reused by all RB1 rows ----
+  {
+    const int nRB = (N + RB1 - 1) / RB1;
+    for (int rb = warp; rb < nRB; rb += NWARP) {
+      float acc[RB1][H];
+#pragma unroll
+      for (int i = 0; i < RB1; ++i)
+#pragma unroll
+        for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
+      const float4* rp[RB1];
+#pragma unroll
+      for (int i = 0; i < RB1; ++i)
+        rp[i] = reinterpret_cast<const float4*>(Mi + (size_t)min(rb * RB1 + i, N - 1) * M);
+      for (int c = lane; c < MC; c += 32) {
+        float4 m4[RB1];
+#pragma unroll
+        for (int i = 0; i < RB1; ++i) m4[i] = __ldcg(rp[i] + c);
+        float4 k4[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) k4[h] = *reinterpret_cast<const float4*>(kS + h * M4 + 4 * c);
+#pragma unroll
+        for (int i = 0; i < RB1; ++i)
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            acc[i][h] = fmaf(m4[i].x, k4[h].x, acc[i][h]);
+            acc[i][h] = fmaf(m4[i].y, k4[h].y, acc[i][h]);
+            acc[i][h] = fmaf(m4[i].z, k4[h].z, acc[i][h]);
+            acc[i][h] = fmaf(m4[i].w, k4[h].w, acc[i][h]);
+          }
+      }
+      // transposing reduction, RB rows (RB*H <= 32 values) at a time: at offset o a lane keeps one half
+      // of its value list and receives the partner's sums of that half; lane L ends with the warp
+      // total of value L = i*H + h (fixed order: deterministic)
+#pragma unroll
+      for (int g = 0; g < RB1 / RB; ++g) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int h = 0; h < H; ++h) v[i * H + h] = acc[g * RB + i][h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int j = 0; j < o; ++j) {
+            const float send = up ? v[j] : v[j + o];
+            const float keep = up ? v[j + o] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        const int vi = lane / H, vh = lane - vi * H;
+        const int n = rb * RB1 + g * RB + vi;
+        if (lane < RB * H && n < N) simS[vh * Npad + n] = v[0];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- addressing on the [H][N] weightings (ntm_cell.py:140-176): WPH warps per head ----
+  {
+    constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
+    constexpr bool multi = (NWARP / H) > 0;
+    const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
+    const int hstep = multi ? H : NWARP;
+    const float* wprev = a.w_in + (size_t)b * a.sw_in;
+    float* wout = a.w_out + (size_t)b * a.sw_out;
+    for (int h = multi ? hgrp : warp; h < H; h += hstep) {
+      float* sh = simS + h * Npad;
+      float* gh = wg + h * Npad;
+      float* red = sRed + h * 3 * WPH;
+      const int nstep = 32 * WPH;
+      const int n0 = 32 * sub + lane;
+      auto head_bar = [&]() {
+        if (WPH > 1) asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(32 * WPH) : "memory");
+        else __syncwarp();
+      };
+      const float gate = sG[h], gamma = sGam[h];
+      float kn = 0.0f;
+      for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+      const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));   // ops.py:152
+      const float beta = sBeta[h];
+      float mx = -INFINITY;
+      for (int n = n0; n < N; n += nstep) {
+        const float x = sh[n] * rs * beta;
+        sh[n] = x;
+        mx = fmaxf(mx, x);
+      }
+      mx = warp_max(mx);
+      if (WPH > 1) {
+        if (lane == 0) red[sub] = mx;
+        head_bar();
+        mx = red[0];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) mx = fmaxf(mx, red[i]);
+      }
+      float sum = 0.0f;
+      for (int n = n0; n < N; n += nstep) {
+        const float e = exp_f(sh[n] - mx);
+        sh[n] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (WPH > 1) {
+        if (lane == 0) red[WPH + sub] = sum;
+        head_bar();
+        sum = red[WPH];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) sum += red[WPH + i];
+      }
+      for (int n = n0; n < N; n += nstep) {
+        const float wc = sh[n] / sum;
+        gh[n] = wc * gate + __ldcg(wprev + h * N + n) * (1.0f - gate);
+      }
+      head_bar();   // the shift reads neighbours' gated weights
+      float psum = 0.0f;
+      for (int n = n0; n < N; n += nstep) {
+        float conv = 0.0f;
+        for (int s = 0; s < S; ++s) {
+          int idx = n + a.shift0 + s;   // circular_shift(x, j)[n] = x[(n + j) mod N], ops.py:216-242
+          idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+          conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
+        }
+        const float pw = exp2f(gamma * log2f(conv));   // conv >= 0, gamma >= 1: pow(conv, gamma), 0 -> 0
+        sh[n] = pw;
+        psum += pw;
+      }
+      psum = warp_sum(psum);
+      if (WPH > 1) {
+        if (lane == 0) red[2 * WPH + sub] = psum;
+        head_bar();
+        psum = red[2 * WPH];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) psum += red[2 * WPH + i];
+      }
+      const float den = psum + 1e-3f;   // ntm_cell.py:175-176
+      for (int n = n0; n < N; n += nstep) {
+        const float wv = sh[n] / den;
+        wnew[h * Npad + n] = wv;
+        wout[h * N + n] = wv;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2 (L2): erase/add write, weighted read, next column norms (ntm_cell.py:193-215).
+  //      lane -> (16-byte column chunk cl of an 8-chunk group, row phase rg); WPC warps share a group ----
+  {
+    const int cl = lane & 7, rg = lane >> 3;
+    const int ncg = (MC + 7) >> 3, WPC = a.WPC;
+    const int rstep = 4 * WPC;
+    for (int si = warp; si < ncg * WPC; si += NWARP) {
+      const int cgi = si / WPC, wsub = si - cgi * WPC;
+      const int c = cgi * 8 + cl;
+      const bool valid = c < MC;
+      const int cc = valid ? c : 0;
+      float4 e4[W], a4[W];
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        e4[h] = *reinterpret_cast<const float4*>(eS + h * M4 + 4 * cc);
+        a4[h] = *reinterpret_cast<const float4*>(aS + h * M4 + 4 * cc);
+      }
+      float4 racc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        for (int nb = wsub * 4 + rg; nb < N; nb += rstep * U2) {
+          float4 mv[U2];
+#pragma unroll
+          for (int u = 0; u < U2; ++u) {
+            const int n = nb + u * rstep;
+            if (n < N) mv[u] = __ldcg(reinterpret_cast<const float4*>(Mi + (size_t)n * M) + c);
+          }
+#pragma unroll
+          for (int u = 0; u < U2; ++u) {
+            const int n = nb + u * rstep;
+            if (n < N) {
+              const float4 m = mv[u];
+              float4 mn;
+              if constexpr (W == 1) {
+                // one write head: M' = M (1 - w e) + w a = M + w (a - M e)
+                const float ww = wnew[R * Npad + n];
+                mn.x = fmaf(ww, fmaf(-m.x, e4[0].x, a4[0].x), m.x);
+                mn.y = fmaf(ww, fmaf(-m.y, e4[0].y, a4[0].y), m.y);
+                mn.z = fmaf(ww, fmaf(-m.z, e4[0].z, a4[0].z), m.z);
+                mn.w = fmaf(ww, fmaf(-m.w, e4[0].w, a4[0].w), m.w);
+              } else {
+                float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < W; ++h) {
+                  const float ww = wnew[(R + h) * Npad + n];
+                  E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
+                  E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
+                  A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
+                  A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
+                }
+                mn.x = fmaf(m.x, E.x, A.x); mn.y = fmaf(m.y, E.y, A.y);
+                mn.z = fmaf(m.z, E.z, A.z); mn.w = fmaf(m.w, E.w, A.w);
+              }
+              const float4 mu = a.write_first ? mn : m;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const float wr = wnew[r * Npad + n];
+                racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
+                racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
+              }
+              csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
+              csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
+              __stcg(reinterpret_cast<float4*>(Mo + (size_t)n * M) + c, mn);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          racc[r].x += __shfl_xor_sync(0xffffffffu, racc[r].x, o);
+          racc[r].y += __shfl_xor_sync(0xffffffffu, racc[r].y, o);
+          racc[r].z += __shfl_xor_sync(0xffffffffu, racc[r].z, o);
+          racc[r].w += __shfl_xor_sync(0xffffffffu, racc[r].w, o);
+        }
+        csq.x += __shfl_xor_sync(0xffffffffu, csq.x, o);
+        csq.y += __shfl_xor_sync(0xffffffffu, csq.y, o);
+        csq.z += __shfl_xor_sync(0xffffffffu, csq.z, o);
+        csq.w += __shfl_xor_sync(0xffffffffu, csq.w, o);
+      }
+      if (valid && rg == 0) {
+        float* xw = xch + (size_t)wsub * (R + 1) * M4;
+#pragma unroll
+        for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(xw + r * M4 + 4 * c) = racc[r];
+        *reinterpret_cast<float4*>(xw + R * M4 + 4 * c) = csq;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- finalize: fixed-order sum over the WPC row slices; read vector + inverse column norms ----
+  {
+    float* ar = a.act_read + (size_t)b * a.s_act;
+    float* ro = a.read_out != nullptr ? a.read_out + (size_t)b * a.s_read : nullptr;
+    for (int i = tid; i < (R + 1) * M; i += NT) {
+      const int r = i / M, d = i - r * M;
+      float s = 0.0f;
+      for (int q = 0; q < a.WPC; ++q) s += xch[((size_t)q * (R + 1) + r) * M4 + d];
+      if (r < R) {
+        ar[i] = s;
+        if (ro) ro[i] = s;
+      } else {
+        cnb[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));   // tf.nn.l2_normalize over N, ops.py:147-150
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TMA-ring variant of the memory kernel (the fast path: M <= 512 columns per 128 threads, H*CPL <= 20).
+// Same arithmetic as mem_step_kernel; what changes is how the memory moves.  The sequence's N x M rows
+// are contiguous in HBM, so they stream through a ring of NS shared-memory stages (RPS rows each) with
+// 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): the copies are issued before the activations
+// run, pass 1 consumes a stage per warp (keys in registers) and refills it itself, the tail of pass 1
+// already prefetches the head of pass 2 (out of L2) behind the addressing phase, and pass 2 updates a
+// stage in place and hands it to a bulk store.  Bytes in flight per CTA = the ring, independent of
+// registers and occupancy -- which is what an HBM-latency-bound stream needs.
+constexpr int TMA_NT = 256;
+constexpr int TMA_LAG = 2;    // a pass-2 stage is reloaded once the store issued TMA_LAG chunks ago has read it
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = s_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol, bool hint) {
+  if (hint)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(pol) : "memory");
+  else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes, uint64_t pol, bool hint) {
+  if (hint)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
+                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes), "l"(pol) : "memory");
+  else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+template <int NKEEP>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NKEEP) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+
+template <int R, int W, int CPL>
+__global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a) {
+  constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32;
+  extern __shared__ float4 mem_smem4[];
+  float* smem = reinterpret_cast<float*>(mem_smem4);
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, M = a.M, M4 = a.M4, MC = a.MC, Npad = a.Npad, S = a.S;
+  const int RPS = a.RPS, NS = a.NS, NCH = a.NCH;
+  float* kS = smem + a.oK;
+  float* eS = smem + a.oE;
+  float* aS = smem + a.oA;
+  float* simS = smem + a.oSim;
+  float* wg = smem + a.oWg;
+  float* wnew = smem + a.oWn;
+  float* wprevS = smem + a.oWp;
+  float* raw = smem + a.oRaw;
+  float* sm = smem + a.oSm;
+  float* ring = smem + a.oRing;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.oBar);   // full[NS], rawbar
+  uint64_t* rawbar = bars + NS;
+  float* sBeta = sm, *sG = sm + H, *sGam = sm + 2 * H, *sSw = sm + 4 * H;
+  float* sPart = sm + 4 * H + H * SMAX;
+  float* sRed = sPart + NWARP * H;
+  const float* Mi = a.Min + (size_t)b * a.sMin;
+  float* Mo = a.Mout + (size_t)b * a.sMout;
+  float* cnb = a.cn + (size_t)b * M4;
+  const size_t stage_floats = (size_t)RPS * M;
+  const bool hint = a.l2_hints != 0;
+  // pass 1 brings the rows in and wants them to survive in L2 until pass 2 re-reads them; after that
+  // re-read, and for the rewritten rows, the next use is a whole timestep (the other sequences) away
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+
+  // chunk sequence number Q: 0..NCH-1 = pass 1, NCH..2*NCH-1 = pass 2; stage Q % NS, parity (Q / NS) & 1
+  auto issue_load = [&](int Q) {
+    const int j = Q < NCH ? Q : Q - NCH;
+    const int r0 = j * RPS;
+    const uint32_t bytes = (uint32_t)(min(RPS, N - r0) * M) * 4u;
+    uint64_t* fb = bars + (Q % NS);
+    mbar_expect_tx(fb, bytes);
+    bulk_load(ring + (size_t)(Q % NS) * stage_floats, Mi + (size_t)r0 * M, bytes, fb, Q < NCH ? pol_keep : pol_drop, hint);
+  };
+
+  if (tid == 0) {
+    for (int s2 = 0; s2 <= NS; ++s2) mbar_init_(bars + s2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_async_smem();
+    mbar_expect_tx(rawbar, (uint32_t)a.PO4 * 4u);
+    bulk_load(raw, a.mc + (size_t)b * a.PO4, (uint32_t)a.PO4 * 4u, rawbar, pol_drop, hint);
+    for (int Q = 0; Q < NS && Q < 2 * NCH; ++Q) issue_load(Q);
+  }
+  {   // weightings entering the step -> shared memory (consumed after pass 1)
+    const float* wprev = a.w_in + (size_t)b * a.sw_in;
+    for (int i = tid; i < H * N; i += NT) {
+      const int h = i / N, n = i - h * N;
+      wprevS[h * Npad + n] = __ldcg(wprev + i);
+    }
+  }
+  __syncthreads();            // barrier inits visible to every thread before anyone polls
+  mbar_wait_(rawbar, 0);
+
+  const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
+            offE = offGam + H, offA = offE + M * W;
+  // ---- activations (ntm_cell.py:133-196) ----
+  {
+    float ss[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) ss[h] = 0.0f;
+    for (int d = tid; d < M4; d += NT) {
+      const bool in = d < M;
+      const float cnd = in ? __ldcg(cnb + d) : 0.0f;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float kv = in ? tanh_f(raw[h * M + d]) : 0.0f;
+        kS[h * M4 + d] = kv * cnd;
+        ss[h] = fmaf(kv, kv, ss[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        eS[h * M4 + d] = in ? sigmoid_f(raw[offE + h * M + d]) : 0.0f;
+        aS[h * M4 + d] = in ? tanh_f(raw[offA + h * M + d]) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
+    }
+  }
+  if (tid < H) {
+    sBeta[tid] = softplus_f(raw[offBeta + tid]);
+    sG[tid] = sigmoid_f(raw[offG + tid]);
+    sGam[tid] = 1.0f + softplus_f(raw[offGam + tid]);
+    float* sp = sSw + tid * SMAX;
+    float mx = -INFINITY;
+    for (int i = 0; i < S; ++i) { sp[i] = raw[offS + tid * S + i]; mx = fmaxf(mx, sp[i]); }
+    float sum = 0.0f;
+    for (int i = 0; i < S; ++i) { sp[i] = exp_f(sp[i] - mx); sum += sp[i]; }
+    const float rsum = __frcp_rn(sum);
+    for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
+  }
+  if (tid == NT - 1) {   // output projection + softmax (ntm_cell.py:220-221)
+    const size_t o = ((size_t)b * a.T + a.t) * a.O;
+    float mx = -INFINITY;
+    for (int i = 0; i < a.O; ++i) mx = fmaxf(mx, raw[a.P + i]);
+    float sum = 0.0f;
+    for (int i = 0; i < a.O; ++i) sum += exp_f(raw[a.P + i] - mx);
+    const float rsum = __frcp_rn(sum);
+    for (int i = 0; i < a.O; ++i) {
+      const float lg = raw[a.P + i];
+      a.logits[o + i] = lg;
+      if (a.outputs) a.outputs[o + i] = exp_f(lg - mx) * rsum;
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 1: a warp owns chunk q = warp, warp + NWARP, ...; keys in registers ----
+  {
+    float4 kr[H][CPL];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        kr[h][j] = c < MC ? *reinterpret_cast<const float4*>(kS + h * M4 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    for (int q = warp; q < NCH; q += NWARP) {
+      const int st = q % NS;
+      mbar_wait_(bars + st, (uint32_t)(q / NS) & 1u);
+      const float* sp = ring + (size_t)st * stage_floats;
+      const int r0 = q * RPS, nr = min(RPS, N - r0);
+      for (int g0 = 0; g0 < nr; g0 += RB) {
+        float acc[RB][H];
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int c = lane + 32 * j;
+          if (c < MC) {
+            float4 m4[RB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+              m4[i] = *reinterpret_cast<const float4*>(sp + (size_t)min(g0 + i, nr - 1) * M + 4 * c);
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+              for (int h = 0; h < H; ++h) {
+                acc[i][h] = fmaf(m4[i].x, kr[h][j].x, acc[i][h]);
+                acc[i][h] = fmaf(m4[i].y, kr[h][j].y, acc[i][h]);
+                acc[i][h] = fmaf(m4[i].z, kr[h][j].z, acc[i][h]);
+                acc[i][h] = fmaf(m4[i].w, kr[h][j].w, acc[i][h]);
+              }
+          }
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int h = 0; h < H; ++h) v[i * H + h] = acc[i][h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int j = 0; j < o; ++j) {
+            const float send = up ? v[j] : v[j + o];
+            const float keep = up ? v[j + o] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        const int vi = lane / H, vh = lane - vi * H;
+        if (lane < RB * H && g0 + vi < nr) simS[vh * Npad + r0 + g0 + vi] = v[0];
+      }
+      // this warp was the stage's only reader: refill it (next pass-1 chunk, or the head of pass 2)
+      __syncwarp();
+      if (lane == 0 && q + NS < 2 * NCH) issue_load(q + NS);
+    }
+  }
+  __syncthreads();
+
+  // ---- addressing (ntm_cell.py:140-176), same as mem_step_kernel but w_prev from shared memory ----
+  {
+    constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
+    constexpr bool multi = (NWARP / H) > 0;
+    const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
+    const int hstep = multi ? H : NWARP;
+    float* wout = a.w_out + (size_t)b * a.sw_out;
+    for (int h = multi ? hgrp : warp; h < H; h += hstep) {
+      float* sh = simS + h * Npad;
+      float* gh = wg + h * Npad;
+      float* red = sRed + h * 3 * WPH;
+      const int nstep = 32 * WPH;
+      const int n0 = 32 * sub + lane;
+      auto head_bar = [&]() {
+        if (WPH > 1) asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(32 * WPH) : "memory");
+        else __syncwarp();
+      };
+      const float gate = sG[h], gamma = sGam[h];
+      float kn = 0.0f;
+      for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+      const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));
+      const float beta = sBeta[h];
+      float mx = -INFINITY;
+      for (int n = n0; n < N; n += nstep) {
+        const float x = sh[n] * rs * beta;
+        sh[n] = x;
+        mx = fmaxf(mx, x);
+      }
+      mx = warp_max(mx);
+      if (WPH > 1) {
+        if (lane == 0) red[sub] = mx;
+        head_bar();
+        mx = red[0];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) mx = fmaxf(mx, red[i]);
+      }
+      float sum = 0.0f;
+      for (int n = n0; n < N; n += nstep) {
+        const float e = exp_f(sh[n] - mx);
+        sh[n] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (WPH > 1) {
+        if (lane == 0) red[WPH + sub] = sum;
+        head_bar();
+        sum = red[WPH];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) sum += red[WPH + i];
+      }
+      for (int n = n0; n < N; n += nstep) {
+        const float wc = sh[n] / sum;
+        gh[n] = wc * gate + wprevS[h * Npad + n] * (1.0f - gate);
+      }
+      head_bar();
+      float psum = 0.0f;
+      for (int n = n0; n < N; n += nstep) {
+        float conv = 0.0f;
+        for (int s = 0; s < S; ++s) {
+          int idx = n + a.shift0 + s;
+          idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+          conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
+        }
+        const float pw = exp2f(gamma * log2f(conv));
+        sh[n] = pw;
+        psum += pw;
+      }
+      psum = warp_sum(psum);
+      if (WPH > 1) {
+        if (lane == 0) red[2 * WPH + sub] = psum;
+        head_bar();
+        psum = red[2 * WPH];
+#pragma unroll
+        for (int i = 1; i < WPH; ++i) psum += red[2 * WPH + i];
+      }
+      const float den = psum + 1e-3f;
+      for (int n = n0; n < N; n += nstep) {
+        const float wv = sh[n] / den;
+        wnew[h * Npad + n] = wv;
+        wout[h * N + n] = wv;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: thread -> (16-byte column chunk c, row phase rp); the stage is updated in place and
+  //      handed to a bulk store ----
+  const int RP = a.RP;
+  const bool worker = tid < RP * MC;
+  const int c = worker ? tid % MC : 0, rp = worker ? tid / MC : 0;
+  float4 racc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    float4 e4[W], a4[W];
+#pragma unroll
+    for (int h = 0; h < W; ++h) {
+      e4[h] = *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c);
+      a4[h] = *reinterpret_cast<const float4*>(aS + h * M4 + 4 * c);
+    }
+    for (int j = 0; j < NCH; ++j) {
+      const int Q = NCH + j, st = Q % NS;
+      mbar_wait_(bars + st, (uint32_t)(Q / NS) & 1u);
+      float* sp = ring + (size_t)st * stage_floats;
+      const int r0 = j * RPS, nr = min(RPS, N - r0);
+      if (worker) {
+        for (int rl = rp; rl < nr; rl += RP) {
+          const int n = r0 + rl;
+          float4* mp = reinterpret_cast<float4*>(sp + (size_t)rl * M) + c;
+          const float4 m = *mp;
+          float4 mn;
+          if constexpr (W == 1) {
+            const float ww = wnew[R * Npad + n];
+            mn.x = fmaf(ww, fmaf(-m.x, e4[0].x, a4[0].x), m.x);
+            mn.y = fmaf(ww, fmaf(-m.y, e4[0].y, a4[0].y), m.y);
+            mn.z = fmaf(ww, fmaf(-m.z, e4[0].z, a4[0].z), m.z);
+            mn.w = fmaf(ww, fmaf(-m.w, e4[0].w, a4[0].w), m.w);
+          } else {
+            float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+              const float ww = wnew[(R + h) * Npad + n];
+              E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
+              E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
+              A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
+              A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
+            }
+            mn.x = fmaf(m.x, E.x, A.x); mn.y = fmaf(m.y, E.y, A.y);
+            mn.z = fmaf(m.z, E.z, A.z); mn.w = fmaf(m.w, E.w, A.w);
+          }
+          const float4 mu = a.write_first ? mn : m;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float wr = wnew[r * Npad + n];
+            racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
+            racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
+          }
+          csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
+          csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
+          *mp = mn;
+        }
+      }
+      fence_async_smem();        // this thread's stage writes -> visible to the bulk store
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store(Mo + (size_t)r0 * M, sp, (uint32_t)(nr * M) * 4u, pol_drop, hint);
+        if (j >= TMA_LAG) {      // the store of chunk j - LAG has read its stage: reload it
+          bulk_wait_read<TMA_LAG>();
+          const int Q2 = Q - TMA_LAG + NS;
+          if (Q2 < 2 * NCH) issue_load(Q2);
+        }
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+  __syncthreads();
+
+  // ---- finalize: partials over the row phases (fixed order) through the now idle ring ----
+  {
+    float* xch = ring;     // [RP][R+1][M4]
+    if (worker) {
+      float* xw = xch + (size_t)rp * (R + 1) * M4;
+#pragma unroll
+      for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(xw + r * M4 + 4 * c) = racc[r];
+      *reinterpret_cast<float4*>(xw + R * M4 + 4 * c) = csq;
+    }
+    __syncthreads();
+    float* ar = a.act_read + (size_t)b * a.s_act;
+    float* ro = a.read_out != nullptr ? a.read_out + (size_t)b * a.s_read : nullptr;
+    for (int i = tid; i < (R + 1) * M; i += NT) {
+      const int r = i / M, d = i - r * M;
+      float s = 0.0f;
+      for (int q = 0; q < RP; ++q) s += xch[((size_t)q * (R + 1) + r) * M4 + d];
+      if (r < R) {
+        ar[i] = s;
+        if (ro) ro[i] = s;
+      } else {
+        cnb[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Once per call: M_in (batch stride may be 0) -> working memory, and its inverse column norms.
+constexpr int INIT_NT = 256;
+__global__ void __launch_bounds__(INIT_NT) init_mem_kernel(const float* __restrict__ Min, long long sMin,
+                                                           float* Mout, long long sMout, float* cn, int N,
+                                                           int M, int M4, int MC, int WPC) {
+  extern __shared__ float4 init_smem4[];
+  float* xch = reinterpret_cast<float*>(init_smem4);   // [WPC][M4]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* Mi = Min + (size_t)b * sMin;
+  float* Mo = Mout + (size_t)b * sMout;
+  const bool copy = (Mi != Mo);
+  const int cl = lane & 7, rg = lane >> 3;
+  const int ncg = (MC + 7) >> 3;
+  for (int si = warp; si < ncg * WPC; si += INIT_NT / 32) {
+    const int cgi = si / WPC, wsub = si - cgi * WPC;
+    const int c = cgi * 8 + cl;
+    const bool valid = c < MC;
+    float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      for (int n = wsub * 4 + rg; n < N; n += 4 * WPC) {
+        const float4 m = __ldcg(reinterpret_cast<const float4*>(Mi + (size_t)n * M) + c);
+        csq.x = fmaf(m.x, m.x, csq.x); csq.y = fmaf(m.y, m.y, csq.y);
+        csq.z = fmaf(m.z, m.z, csq.z); csq.w = fmaf(m.w, m.w, csq.w);
+        if (copy) __stcg(reinterpret_cast<float4*>(Mo + (size_t)n * M) + c, m);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      csq.x += __shfl_xor_sync(0xffffffffu, csq.x, o);
+      csq.y += __shfl_xor_sync(0xffffffffu, csq.y, o);
+      csq.z += __shfl_xor_sync(0xffffffffu, csq.z, o);
+      csq.w += __shfl_xor_sync(0xffffffffu, csq.w, o);
+    }
+    if (valid && rg == 0) *reinterpret_cast<float4*>(xch + (size_t)wsub * M4 + 4 * c) = csq;
+  }
+  __syncthreads();
+  for (int d = tid; d < M; d += INIT_NT) {
+    float s = 0.0f;
+    for (int q = 0; q < WPC; ++q) s += xch[(size_t)q * M4 + d];
+    cn[(size_t)b * M4 + d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+  }
+}
+
+struct SmallInitArgs {
+  int H, N, R, M, C, L;
+  const float *w_in, *read_in, *ctrl_in;
+  long long sw_in, sread_in, sctrl_in;
+  float *w_out, *ctrl_out;
+  long long sw_out, sctrl_out;
+  float* act[MAXL];
+  int actK[MAXL];
+  float *hC, *hH, *hRead;     // slot 0 of the training history (or null)
+  long long B;
+};
+// weightings, read vectors and controller state -> working buffers (one CTA per sequence)
+__global__ void init_small_kernel(const SmallInitArgs a) {
+  const long long b = blockIdx.x;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const float* wi = a.w_in + b * a.sw_in;
+  float* wo = a.w_out + b * a.sw_out;
+  if (wi != wo)
+    for (int i = tid; i < a.H * a.N; i += NT) wo[i] = wi[i];
+  for (int i = tid; i < a.R * a.M; i += NT) {
+    const float v = a.read_in[b * a.sread_in + i];
+    a.act[0][b * a.actK[0] + i] = v;
+    if (a.hRead) a.hRead[b * (long long)(a.R * a.M) + i] = v;
+  }
+  for (int i = tid; i < a.L * a.C; i += NT) {
+    const int l = i / a.C, u = i - l * a.C;
+    const float c = a.ctrl_in[b * a.sctrl_in + (2 * l) * a.C + u];
+    const float h = a.ctrl_in[b * a.sctrl_in + (2 * l + 1) * a.C + u];
+    a.ctrl_out[b * a.sctrl_out + (2 * l) * a.C + u] = c;
+    a.ctrl_out[b * a.sctrl_out + (2 * l + 1) * a.C + u] = h;
+    a.act[l][b * a.actK[l] + (a.actK[l] - a.C) + u] = h;
+    if (a.hC) a.hC[(b * a.L + l) * a.C + u] = c;
+    if (a.hH) a.hH[(b * a.L + l) * a.C + u] = h;
+  }
+}
+
+// BasicLSTMCell gates for all sequences (TF 1.0/1.1: i, j, f, o = split4(z); c' = c*sig(f) +
+// sig(i)*tanh(j); h' = tanh(c')*sig(o)); z = hoisted x-projection (layer 0, bias folded in) or bias
+// plus the K-slice partials of the controller GEMM in slice order.
+struct LstmArgs {
+  long long B; int C, L, l, T, t, KS; long long slab;
+  const float* xw; const float* bias; const float* part;
+  float* ctrl; long long sctrl;          // state_out.controller_state, updated in place
+  float* act_self; int actK_self;        // h -> recurrent input of this layer (last C columns)
+  float* act_next; int actK_next;        // h -> first C columns of the next layer's input (or null)
+  float *hZ, *hC, *hH;                   // training history (or null)
+};
+__global__ void lstm_stream_kernel(const LstmArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.C) return;
+  const long long b = i / a.C;
+  const int u = (int)(i - b * a.C), C = a.C;
+  float z[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = q * C + u;
+    float v = (a.l == 0) ? __ldg(a.xw + (b * a.T + a.t) * (long long)(4 * C) + col) : __ldg(a.bias + col);
+    for (int ks = 0; ks < a.KS; ++ks) v += __ldcg(a.part + (size_t)ks * a.slab + b * (long long)(4 * C) + col);
+    z[q] = v;
+    if (a.hZ) a.hZ[((((size_t)a.t * a.B + b) * a.L + a.l) * 4 + q) * C + u] = v;
+  }
+  float* cp = a.ctrl + b * a.sctrl + (2 * a.l) * C + u;
+  const float c_prev = *cp;
+  const float c_new = c_prev * sigmoid_f(z[2]) + sigmoid_f(z[0]) * tanh_f(z[1]);
+  const float h_new = tanh_f(c_new) * sigmoid_f(z[3]);
+  cp[0] = c_new;
+  cp[C] = h_new;
+  if (a.hC) a.hC[(((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u] = c_new;
+  if (a.hH) a.hH[(((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u] = h_new;
+  a.act_self[b * a.actK_self + (a.actK_self - C) + u] = h_new;
+  if (a.act_next) a.act_next[b * a.actK_next + u] = h_new;
+}
+
+// ------------------------------------------------------------------------------------- host side --
+constexpr int MEM_NT = 256;
+int g_mem_occ = 0;
+
+template <int R, int W, int NT, int MINB>
+cudaError_t launch_mem_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(mem_step_kernel<R, W, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_kernel<R, W, NT, MINB>, NT, smem);
+  }
+  mem_step_kernel<R, W, NT, MINB><<<(unsigned)B, NT, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template <int R, int W>
+cudaError_t launch_mem_rw(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+#ifdef NTM_EXP_MEM_VARIANTS
+  if constexpr (R == 4 && W == 1) {
+    static const int v = getenv("NTM_B200_MEM_VARIANT") ? atoi(getenv("NTM_B200_MEM_VARIANT")) : 0;
+    if (v == 1) return launch_mem_v<R, W, 256, 2>(a, B, smem, stream);
+    if (v == 2) return launch_mem_v<R, W, 256, 3>(a, B, smem, stream);
+  }
+#endif
+  return launch_mem_v<R, W, MEM_NT, 1>(a, B, smem, stream);
+}
+template <int R>
+cudaError_t launch_mem_r(int W, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  switch (W) {
+    case 1: return launch_mem_rw<R, 1>(a, B, smem, stream);
+    case 2: return launch_mem_rw<R, 2>(a, B, smem, stream);
+    case 3: return launch_mem_rw<R, 3>(a, B, smem, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_mem(int R, int W, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  switch (R) {
+    case 1: return launch_mem_r<1>(W, a, B, smem, stream);
+    case 2: return launch_mem_r<2>(W, a, B, smem, stream);
+    case 3: return launch_mem_r<3>(W, a, B, smem, stream);
+    case 4: return launch_mem_r<4>(W, a, B, smem, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ---- TMA-ring kernel dispatch ----
+template <int R, int W, int CPL>
+cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  if constexpr ((R + W) * CPL > 20) {
+    return cudaErrorInvalidValue;
+  } else {
+    static int configured = 0;
+    if (configured < smem) {
+      cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_tma_kernel<R, W, CPL>, TMA_NT, smem);
+    }
+    mem_step_tma_kernel<R, W, CPL><<<(unsigned)B, TMA_NT, smem, stream>>>(a);
+    return cudaGetLastError();
+  }
+}
+template <int R, int W>
+cudaError_t launch_tma_rw(int CPL, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  switch (CPL) {
+    case 1: return launch_tma_v<R, W, 1>(a, B, smem, stream);
+    case 2: return launch_tma_v<R, W, 2>(a, B, smem, stream);
+    case 4: return launch_tma_v<R, W, 4>(a, B, smem, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+template <int R>
+cudaError_t launch_tma_r(int W, int CPL, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  switch (W) {
+    case 1: return launch_tma_rw<R, 1>(CPL, a, B, smem, stream);
+    case 2: return launch_tma_rw<R, 2>(CPL, a, B, smem, stream);
+    case 3: return launch_tma_rw<R, 3>(CPL, a, B, smem, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_tma(int R, int W, int CPL, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  switch (R) {
+    case 1: return launch_tma_r<1>(W, CPL, a, B, smem, stream);
+    case 2: return launch_tma_r<2>(W, CPL, a, B, smem, stream);
+    case 3: return launch_tma_r<3>(W, CPL, a, B, smem, stream);
+    case 4: return launch_tma_r<4>(W, CPL, a, B, smem, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+// 0 when the TMA-ring kernel does not cover the shape (then the generic register-streaming kernel runs)
+int tma_cpl(int H, int MC) {
+  const int cpl = MC <= 32 ? 1 : (MC <= 64 ? 2 : (MC <= 128 ? 4 : 0));
+  if (cpl == 0 || H * cpl > 20) return 0;
+  return cpl;
+}
+
+thread_local std::vector<cudaEvent_t> g_sev;
+thread_local int g_sev_steps = 0;
+
+}  // namespace
+
+bool stream_supported(const ntm_b200_shape* s, int nsm) {
+  if (s->mem_dim % 4 != 0) return false;
+  const int C = s->controller_hidden_size, H = s->read_head_size + s->write_head_size;
+  const int S = 2 * s->shift_range + 1;
+  const int P = H * s->mem_dim + 3 * H + S * H + 2 * s->mem_dim * s->write_head_size;
+  const int PO4 = round_up(P + s->output_dim, 4);
+  // the tile kernel needs (column tiles x K-slices) <= SMs for every GEMM
+  for (int l = 0; l < s->controller_num_layers; ++l) {
+    const int K = (l == 0) ? s->read_head_size * s->mem_dim + C : 2 * C;
+    if ((K & 1) != 0) return false;                       // 8-byte aligned activation rows
+    if (ceil_div(4 * C, 128) * gemm_tc_slices(K) > nsm) return false;
+  }
+  if (gemm_tc_slices(C) != 1) return false;               // head parameters: one slice (bias in the GEMM)
+  if (ceil_div(PO4, 128) > nsm) return false;
+  // shared memory of the memory kernel
+  const int M4 = s->mem_dim, Npad = round_up(s->mem_size, 4);
+  const long long fl = (long long)(H + 2 * s->write_head_size) * M4 + 3ll * H * Npad + 256 +
+                       (long long)(MEM_NT / 32) * (s->read_head_size + 1) * M4;
+  return 4 * fl <= 200 * 1024;
+}
+
+void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWorkspace* ws) {
+  const int C = s->controller_hidden_size, L = s->controller_num_layers;
+  const int H = s->read_head_size + s->write_head_size, S = 2 * s->shift_range + 1;
+  const int P = H * s->mem_dim + 3 * H + S * H + 2 * s->mem_dim * s->write_head_size;
+  const int PO4 = round_up(P + s->output_dim, 4);
+  long long o = 0;
+  auto take = [&](long long bytes) { long long r = o; o = align_up_ll(o + bytes, 256); return r; };
+  int ksmax = 1;
+  for (int l = 0; l < L; ++l) {
+    ws->actK[l] = (l == 0) ? s->read_head_size * s->mem_dim + C : 2 * C;
+    ws->ksA[l] = gemm_tc_slices(ws->actK[l]);
+    ksmax = std::max(ksmax, ws->ksA[l]);
+    ws->off_act[l] = take(4ll * B * ws->actK[l]);
+  }
+  ws->ksC = 1;
+  ws->slabA = B * 4ll * C;
+  ws->slabC = B * (long long)PO4;
+  ws->off_partA = take(4ll * ksmax * ws->slabA);
+  ws->off_mc = take(4ll * ws->slabC);
+  ws->off_cn = take(4ll * B * round_up(s->mem_dim, 4));
+  ws->off_xw = take(4ll * B * T * 4 * C);
+  ws->total = o;
+}
+
+int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const float* wC, const float* bC,
+                   long long B, long long T, const float* xw, const ntm_b200_state* in,
+                   const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
+                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof) {
+  const int C = s->controller_hidden_size, L = s->controller_num_layers;
+  const int R = s->read_head_size, W = s->write_head_size, H = R + W, S = 2 * s->shift_range + 1;
+  const int N = s->mem_size, M = s->mem_dim, M4 = round_up(M, 4), MC = M4 / 4, Npad = round_up(N, 4);
+  const int P = H * M + 3 * H + S * H + 2 * M * W, PO = P + s->output_dim, PO4 = round_up(PO, 4);
+  cudaError_t e;
+  float* act[MAXL];
+  for (int l = 0; l < L; ++l) act[l] = reinterpret_cast<float*>(wsb + ws.off_act[l]);
+  float* partA = reinterpret_cast<float*>(wsb + ws.off_partA);
+  float* mcbuf = reinterpret_cast<float*>(wsb + ws.off_mc);
+  float* cn = reinterpret_cast<float*>(wsb + ws.off_cn);
+  const bool hM = hist && hist->M_prev, hW = hist && hist->w_prev, hP = hist && hist->params;
+
+  if (prof) {
+    const size_t need = 4 * (size_t)T + 2;
+    while (g_sev.size() < need) {
+      cudaEvent_t ev;
+      if ((e = cudaEventCreate(&ev)) != cudaSuccess) return set_cuda_error_ext(e, "cudaEventCreate");
+      g_sev.push_back(ev);
+    }
+    g_sev_steps = 0;
+    cudaEventRecord(g_sev[0], stream);
+  }
+
+  // ---- init: working copies of the state, inverse column norms of the initial memory ----
+  const int ncg = (MC + 7) / 8;
+  const int WPCi = std::max(1, (INIT_NT / 32) / ncg);
+  float* M0 = hM ? hist->M_prev : out->M;                      // memory entering step 0
+  const long long sM0 = hM ? (long long)N * M : out->stride_M;
+  init_mem_kernel<<<(unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(in->M, in->stride_M, M0, sM0, cn, N, M, M4, MC, WPCi);
+  count_launch();
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_mem_kernel");
+  {
+    SmallInitArgs ia{};
+    ia.H = H; ia.N = N; ia.R = R; ia.M = M; ia.C = C; ia.L = L; ia.B = B;
+    ia.w_in = in->w; ia.read_in = in->read; ia.ctrl_in = in->controller_state;
+    ia.sw_in = in->stride_w; ia.sread_in = in->stride_read; ia.sctrl_in = in->stride_controller_state;
+    ia.w_out = hW ? hist->w_prev : out->w; ia.sw_out = hW ? (long long)H * N : out->stride_w;
+    ia.ctrl_out = out->controller_state; ia.sctrl_out = out->stride_controller_state;
+    for (int l = 0; l < L; ++l) { ia.act[l] = act[l]; ia.actK[l] = ws.actK[l]; }
+    ia.hC = hist ? hist->c : nullptr; ia.hH = hist ? hist->h : nullptr; ia.hRead = hist ? hist->read : nullptr;
+    init_small_kernel<<<(unsigned)B, 256, 0, stream>>>(ia);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_small_kernel");
+  }
+  if (prof) cudaEventRecord(g_sev[1], stream);
+
+  // ---- shared-memory carve-up of the memory kernel ----
+  MemArgs ma{};
+  {
+    const int nwarp = MEM_NT / 32;
+    ma.WPC = std::max(1, nwarp / ncg);
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
+    ma.oK = take(H * M4); ma.oE = take(W * M4); ma.oA = take(W * M4);
+    ma.oSim = take(H * Npad); ma.oWg = take(H * Npad); ma.oWn = take(H * Npad);
+    ma.oSm = take(4 * H + H * SMAX + nwarp * H + 3 * H * std::max(1, nwarp / H) + 8);
+    ma.oX = take(ma.WPC * (R + 1) * M4);
+    const int smem = 4 * o;
+    // TMA-ring kernel (when it covers the shape): its own carve-up replaces the generic one
+    int smem_tma = 0;
+    const int cpl = (getenv("NTM_B200_NO_TMA_RING") == nullptr) ? tma_cpl(H, MC) : 0;
+    if (cpl) {
+      int o2 = 0;
+      auto take2 = [&](int n) { int r = o2; o2 += round_up(n, 4); return r; };
+      ma.oK = take2(H * M4); ma.oE = take2(W * M4); ma.oA = take2(W * M4);
+      ma.oSim = take2(H * Npad); ma.oWg = take2(H * Npad); ma.oWn = take2(H * Npad); ma.oWp = take2(H * Npad);
+      ma.oRaw = take2(PO4);
+      ma.oSm = take2(4 * H + H * SMAX + (TMA_NT / 32) * H + 3 * H * std::max(1, (TMA_NT / 32) / H) + 8);
+      ma.NS = 8;
+      ma.RPS = std::min(N, std::max(1, 2048 / M));
+      ma.NCH = ceil_div(N, ma.RPS);
+      ma.RP = std::max(1, TMA_NT / MC);
+      ma.oBar = take2(2 * (ma.NS + 1) + 2);
+      o2 = round_up(o2, 32);                      // 128-byte aligned ring
+      ma.oRing = o2;
+      o2 += std::max(ma.NS * ma.RPS * M, ma.RP * (R + 1) * M4);
+      smem_tma = 4 * o2;
+      ma.l2_hints = getenv("NTM_B200_NO_L2_HINTS") == nullptr ? 1 : 0;
+    }
+    ma.N = N; ma.M = M; ma.M4 = M4; ma.MC = MC; ma.Npad = Npad; ma.S = S;
+    ma.shift0 = -((S + 1) / 2);   // Python-2 floor(-S/2), ops.py:204
+    ma.P = P; ma.PO4 = PO4; ma.O = s->output_dim; ma.write_first = s->write_first ? 1 : 0; ma.T = (int)T;
+    ma.nslab = 1; ma.slab = 0; ma.bias = nullptr;
+    ma.cn = cn; ma.act_read = act[0]; ma.s_act = ws.actK[0];
+    ma.logits = logits; ma.outputs = outputs;
+
+    for (long long t = 0; t < T; ++t) {
+      const bool last = (t == T - 1);
+      if (prof) cudaEventRecord(g_sev[2 + 4 * t + 0], stream);
+      // ---- controller: per layer GEMM (tensor cores) + gates ----
+      for (int l = 0; l < L; ++l) {
+        const float* wl = w->lstm_w[l] + (l == 0 ? (size_t)s->input_dim * 4 * C : 0);
+        int st = gemm_tc(act[l], ws.actK[l], wl, 4 * C, nullptr, partA, 4 * C, ws.slabA, B, ws.actK[l], 4 * C,
+                         ws.ksA[l], nsm, stream);
+        count_launch();
+        if (st != 0) return set_cuda_error_ext(cudaGetLastError(), "gemm_tc(controller)");
+        LstmArgs la{};
+        la.B = B; la.C = C; la.L = L; la.l = l; la.T = (int)T; la.t = (int)t; la.KS = ws.ksA[l]; la.slab = ws.slabA;
+        la.xw = xw; la.bias = w->lstm_b[l]; la.part = partA;
+        la.ctrl = out->controller_state; la.sctrl = out->stride_controller_state;
+        la.act_self = act[l]; la.actK_self = ws.actK[l];
+        la.act_next = (l + 1 < L) ? act[l + 1] : nullptr; la.actK_next = (l + 1 < L) ? ws.actK[l + 1] : 0;
+        la.hZ = hist ? hist->z : nullptr; la.hC = hist ? hist->c : nullptr; la.hH = hist ? hist->h : nullptr;
+        const long long tot = B * C;
+        lstm_stream_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(la);
+        count_launch();
+        if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "lstm_stream_kernel");
+      }
+      if (prof) cudaEventRecord(g_sev[2 + 4 * t + 1], stream);
+      // ---- head parameters + logits: one GEMM, bias folded in ----
+      float* mc_t = hP ? hist->params + (size_t)t * B * PO4 : mcbuf;
+      {
+        int st = gemm_tc(act[L - 1] + (ws.actK[L - 1] - C), ws.actK[L - 1], wC, PO4, bC, mc_t, PO4, 0, B, C, PO4, 1,
+                         nsm, stream);
+        count_launch();
+        if (st != 0) return set_cuda_error_ext(cudaGetLastError(), "gemm_tc(head parameters)");
+      }
+      if (prof) cudaEventRecord(g_sev[2 + 4 * t + 2], stream);
+      // ---- fused addressing + memory update ----
+      ma.t = (int)t; ma.mc = mc_t;
+      ma.Min = hM ? hist->M_prev + (size_t)t * B * N * M : out->M;
+      ma.sMin = hM ? (long long)N * M : out->stride_M;
+      ma.Mout = (hM && !last) ? hist->M_prev + (size_t)(t + 1) * B * N * M : out->M;
+      ma.sMout = (hM && !last) ? (long long)N * M : out->stride_M;
+      if (hW) {
+        ma.w_in = hist->w_prev + (size_t)t * B * H * N; ma.sw_in = (long long)H * N;
+        ma.w_out = last ? out->w : hist->w_prev + (size_t)(t + 1) * B * H * N;
+        ma.sw_out = last ? out->stride_w : (long long)H * N;
+      } else {
+        ma.w_in = out->w; ma.sw_in = out->stride_w; ma.w_out = out->w; ma.sw_out = out->stride_w;
+      }
+      if (hist && hist->read) {
+        ma.read_out = hist->read + (size_t)(t + 1) * B * R * M; ma.s_read = (long long)R * M;
+      } else {
+        ma.read_out = last ? out->read : nullptr; ma.s_read = out->stride_read;
+      }
+      e = cpl ? launch_tma(R, W, cpl, ma, B, smem_tma, stream) : launch_mem(R, W, ma, B, smem, stream);
+      count_launch();
+      if (e != cudaSuccess) return set_cuda_error_ext(e, "mem_step_kernel");
+      if (prof) cudaEventRecord(g_sev[2 + 4 * t + 3], stream);
+    }
+    if (hist && hist->read) {   // the state copy of the last read vectors
+      e = cudaMemcpy2DAsync(out->read, 4 * out->stride_read, hist->read + (size_t)T * B * R * M, 4ll * R * M,
+                            4ll * R * M, B, cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) return set_cuda_error_ext(e, "cudaMemcpy2DAsync(read)");
+    }
+  }
+  if (prof) g_sev_steps = (int)T;
+  return NTM_B200_OK;
+}
+
+int stream_mem_occupancy() { return g_mem_occ; }
+
+int stream_last_ms(float* out4) {
+  out4[0] = out4[1] = out4[2] = out4[3] = 0.0f;
+  if (g_sev_steps <= 0) return 0;
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, g_sev[0], g_sev[1]);
+  out4[3] = ms;
+  for (int t = 0; t < g_sev_steps; ++t) {
+    const cudaEvent_t* ev = &g_sev[2 + 4 * t];
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) out4[0] += ms;
+    if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) out4[1] += ms;
+    if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) out4[2] += ms;
+  }
+  return g_sev_steps;
+}
+
+}  // namespace ntm_b200

@@ -1,0 +1,48 @@
+// ntm_b200_stream.h -- host interface of the streaming (throughput) mode of the NTM sequence path.
+//
+// The persistent kernel (ntm_b200_seq_kernel.cuh) keeps each sequence's memory in shared memory, which
+// caps the sequences in flight at ~74 (C2 shapes) however large the batch is.  For batches far beyond
+// that the same step is run over ALL sequences of the shard in lockstep: the dense projections become
+// large tensor-core GEMMs and the memory is streamed from HBM by one fused addressing kernel per
+// timestep (one read + one write of M per sequence-step; the second read hits L2).  See DESIGN.md s4.4.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ntm_b200.h"
+#include "ntm_b200_params.h"
+
+namespace ntm_b200 {
+
+struct StreamWorkspace {
+  long long off_act[MAXL], off_partA, off_mc, off_cn, off_xw, total;
+  long long slabA, slabC;       // floats per K-slice slab
+  int ksA[MAXL], ksC;           // K-slices of each controller GEMM / of the head-parameter GEMM
+  int actK[MAXL];
+};
+
+// true when the shape is one the streaming kernels cover (M % 4 == 0, GEMM widths within the tile kernel)
+bool stream_supported(const ntm_b200_shape* s, int nsm);
+void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWorkspace* ws);
+
+// Runs T steps for B sequences.  xw = hoisted x-projection [B,T,4C] (already computed on `stream`),
+// wC/bC = packed [C,PO4] head-parameter + output projection.  Returns an ntm_b200_status.
+// `hist` (may be null) = training history buffers (ntm_b200.h); in this mode M_prev[t] IS the working
+// memory of step t (pass 2 writes slot t+1), so recording it costs no extra traffic.
+int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const float* wC, const float* bC,
+                   long long B, long long T, const float* xw, const ntm_b200_state* in,
+                   const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
+                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof);
+
+// profiling (after the stream was synchronised): {controller GEMM + LSTM, head-parameter GEMM, memory
+// kernel, init} summed over the T steps, in ms; returns the number of memory-kernel launches (0 = none)
+int stream_last_ms(float* out4);
+// co-resident CTAs per SM of the memory kernel last configured (occupancy query)
+int stream_mem_occupancy();
+
+// defined in ntm_b200.cu (the tcgen05 tile kernel lives in a header with internal linkage state)
+int gemm_tc(const float* x, int ldx, const float* w, int ldw, const float* bias, float* out, int ldo,
+            long long slab, long long rows, int K, int ncols, int kslices, int nsm, cudaStream_t stream);
+int gemm_tc_slices(int K);
+int set_cuda_error_ext(cudaError_t e, const char* where);
+
+}  // namespace ntm_b200

@@ -25,18 +25,35 @@ constexpr int XT_THREADS = 512;
 constexpr int XT_ROWS = 128;          // frames per row block (MMA N)
 constexpr int XT_MAX_KATOMS = 10;     // K <= 640
 
+// out[ks][r, j] = x[r, k0 .. k0+kw) @ w[k0 .. k0+kw, j] (+ bias[j] when bias != null; K-slice ks starts
+// at k0 = ks * kw).  x rows are ldx floats apart, out rows ldo floats apart, slice ks writes its own
+// slab at out + ks * slab (the consumer sums the slabs in slice order: deterministic split-K).
 struct XprojTcArgs {
   const float* x; const float* w; const float* bias; float* out;
   long long rows; int D; int ncols; int ldw;
   int ntiles, ngroups, katoms;
+  int ldx, ldo, kslices, kw;   // D = total K; kw = slice width (multiple of 64 when kslices > 1)
+  long long slab;
+  int vec2;                    // x rows and slice starts are 8-byte aligned
 };
 
-__global__ void __launch_bounds__(XT_THREADS, 1) xproj_tc_kernel(const XprojTcArgs a) {
+__global__ void __launch_bounds__(XT_THREADS, 1) xproj_tc_kernel(const XprojTcArgs a0) {
+  // this CTA's K-slice as a self-contained problem
+  XprojTcArgs a = a0;
+  const int kslice = (blockIdx.x / a0.ntiles) % a0.kslices;
+  {
+    const int k0 = kslice * a0.kw;
+    a.D = min(a0.kw, a0.D - k0);
+    a.x = a0.x + k0;
+    a.w = a0.w + (size_t)k0 * a0.ldw;
+    a.out = a0.out + (size_t)kslice * a0.slab;
+    a.katoms = (a.D + 63) / 64;
+  }
   using namespace umma;
   extern __shared__ __align__(16) uint8_t xt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xt_smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x % a.ntiles, group = blockIdx.x / a.ntiles;
+  const int tile = blockIdx.x % a.ntiles, group = blockIdx.x / (a.ntiles * a.kslices);
   const int katoms = a.katoms, Kpad = katoms * 64;
   const int ksteps = (a.D + 15) / 16;                     // 16-wide MMA k-steps that hold real data
   uint8_t* sWlo = smem;                                   // [katoms][128 cols][128 B]
@@ -75,7 +92,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xproj_tc_kernel(const XprojTcAr
     tmem_wait_st();
   }
   const int jcol = tile * 128 + 32 * (warp & 3) + lane;
-  const float bias = (jcol < a.ncols) ? __ldg(a.bias + jcol) : 0.0f;
+  const float bias = (a.bias != nullptr && jcol < a.ncols) ? __ldg(a.bias + jcol) : 0.0f;
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -105,8 +122,8 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xproj_tc_kernel(const XprojTcAr
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.0f;
         if (r0 + r < a.rows) {
-          const float* src = a.x + (r0 + r) * (long long)a.D + k;
-          if (((a.D & 1) == 0) && k + 8 <= a.D) {
+          const float* src = a.x + (r0 + r) * (long long)a.ldx + k;
+          if (a.vec2 && k + 8 <= a.D) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 t = __ldg(reinterpret_cast<const float2*>(src) + e);
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xproj_tc_kernel(const XprojTcAr
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const long long r = r0 + cq0 + c + e;
-            if (r < a.rows) a.out[r * (long long)a.ncols + jcol] = __uint_as_float(v[e]) + bias;
+            if (r < a.rows) a.out[r * (long long)a.ldo + jcol] = __uint_as_float(v[e]) + bias;
           }
         }
       }
@@ -180,17 +197,23 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xproj_tc_kernel(const XprojTcAr
 }
 
 // Returns 0 on success, 1 on launch failure, -1 if the shape is outside what the kernel supports
-// (the caller then uses the SIMT kernel).
-inline int launch_xproj_tc(const float* x, const float* w0, const float* b0, float* xw, long long rows,
-                           int D, int ncols, int nsm, cudaStream_t stream) {
+// (the caller then uses the SIMT kernel).  General form: split-K over `kslices` slabs.
+inline int launch_gemm_tc(const float* x, int ldx, const float* w, int ldw, const float* bias, float* out,
+                          int ldo, long long slab, long long rows, int K, int ncols, int kslices, int nsm,
+                          cudaStream_t stream) {
   XprojTcArgs a{};
-  a.x = x; a.w = w0; a.bias = b0; a.out = xw; a.rows = rows; a.D = D; a.ncols = ncols; a.ldw = ncols;
-  a.katoms = (D + 63) / 64;
+  a.x = x; a.w = w; a.bias = bias; a.out = out; a.rows = rows; a.D = K; a.ncols = ncols; a.ldw = ldw;
+  a.ldx = ldx; a.ldo = ldo; a.kslices = kslices; a.slab = slab;
+  a.kw = kslices > 1 ? ((K + kslices - 1) / kslices + 63) / 64 * 64 : K;
+  if (kslices > 1 && (long long)(kslices - 1) * a.kw >= K) return -1;   // an empty last slice
+  a.katoms = (a.kw + 63) / 64;
   if (a.katoms > XT_MAX_KATOMS) return -1;
+  a.vec2 = ((ldx & 1) == 0 && (kslices == 1 || (a.kw & 1) == 0) && (reinterpret_cast<uintptr_t>(x) & 7) == 0) ? 1 : 0;
   a.ntiles = (ncols + 127) / 128;
-  if (a.ntiles > nsm) return -1;
+  const int units = a.ntiles * kslices;
+  if (units > nsm) return -1;
   const long long nrb = (rows + XT_ROWS - 1) / XT_ROWS;
-  a.ngroups = (int)(nrb < (long long)(nsm / a.ntiles) ? nrb : (long long)(nsm / a.ntiles));
+  a.ngroups = (int)(nrb < (long long)(nsm / units) ? nrb : (long long)(nsm / units));
   if (a.ngroups < 1) a.ngroups = 1;
   const int smem = 1024 + a.katoms * 128 * 128 + 2 * 2 * XT_ROWS * 128;
   static int configured = 0;
@@ -201,8 +224,20 @@ inline int launch_xproj_tc(const float* x, const float* w0, const float* b0, flo
     }
     configured = smem;
   }
-  xproj_tc_kernel<<<a.ntiles * a.ngroups, XT_THREADS, smem, stream>>>(a);
+  xproj_tc_kernel<<<units * a.ngroups, XT_THREADS, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Smallest number of K-slices whose (64-rounded) width fits the resident weight tile.
+inline int gemm_tc_kslices(int K) {
+  int ks = 1;
+  while (((K + ks - 1) / ks + 63) / 64 > XT_MAX_KATOMS) ++ks;
+  return ks;
+}
+
+inline int launch_xproj_tc(const float* x, const float* w0, const float* b0, float* xw, long long rows,
+                           int D, int ncols, int nsm, cudaStream_t stream) {
+  return launch_gemm_tc(x, D, w0, ncols, b0, xw, ncols, 0, rows, D, ncols, 1, nsm, stream);
 }
 
 }  // namespace ntm_b200

@@ -17,17 +17,21 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-@pytest.fixture(autouse=True, params=["tensor", "simt"])
+@pytest.fixture(autouse=True, params=["tensor", "simt", "stream"])
 def gemm_path(request):
-    """Every parity test runs on both controller-GEMM paths: the tcgen05 path (weights
-    resident in TMEM; the library still picks SIMT where the tiles do not fit) and the
-    forced fp32 SIMT path."""
+    """Every parity test runs on both controller-GEMM paths of the persistent kernel -- the tcgen05
+    path (weights resident in TMEM; the library still picks SIMT where the tiles do not fit) and the
+    forced fp32 SIMT path -- and in the streaming mode (large-batch path: lockstep over the shard,
+    tensor-core GEMMs + the fused HBM-streaming addressing kernel; shapes it does not cover, and
+    calls that ask for debug taps, fall back to the persistent kernel)."""
+    os.environ["NTM_B200_MODE"] = "stream" if request.param == "stream" else "resident"
     if request.param == "simt":
         os.environ["NTM_B200_DISABLE_TC"] = "1"
     else:
         os.environ.pop("NTM_B200_DISABLE_TC", None)
     yield request.param
     os.environ.pop("NTM_B200_DISABLE_TC", None)
+    os.environ.pop("NTM_B200_MODE", None)
 
 CASES = ["small_r2w1_l2", "small_writefirst_s2", "c1_copy", "c2_tracker_b2t4", "defaults_r3w3_l3"]
 
@@ -148,9 +152,10 @@ def test_c2_tracker_full_config(gemm_path):
     kw, B, T = O.CONFIGS["c2_tracker"]
     errs, _, _ = run_vs_oracle(O.NTMShape(**kw), B, T, 22)
     info = _cabi.last_launch_info()
-    assert info["tensor_path"] == (1 if gemm_path == "tensor" else 0), info
-    assert info["sequences_resident"] == 64 and info["teams"] == 1 and info["cluster_size"] == 2
-    assert info["xproj_tensor_path"] == (1 if gemm_path == "tensor" else 0)
+    assert info["tensor_path"] == (0 if gemm_path == "simt" else 1), info
+    assert info["sequences_resident"] == 64 and info["teams"] == 1
+    assert info["cluster_size"] == (1 if gemm_path == "stream" else 2)
+    assert info["xproj_tensor_path"] == (0 if gemm_path == "simt" else 1)
     assert max(errs.values()) <= TOL, errs
 
 
@@ -354,3 +359,25 @@ def test_cabi_error_paths_on_device():
     assert lib.ntm_b200_forward_seq(*args(ws.numel(), x.data_ptr())) == 0
     assert lib.ntm_b200_finish(ws.data_ptr(), None) == 0
     assert torch.isfinite(logits).all()
+
+
+def test_streaming_mode_is_used(gemm_path):
+    """C2 shapes with NTM_B200_MODE=stream must really run the streaming kernels (not fall back),
+    and the automatic choice must pick streaming for a batch of many waves and the persistent kernel
+    for a batch of one wave."""
+    from ntm_tracker_b200 import _cabi
+    kw, _, _ = O.CONFIGS["c2_tracker"]
+    s = O.NTMShape(**kw)
+    params = O.init_params(s, 5, 0.05)
+    x = O.tracker_inputs(3, 2, 17)
+    trk = make_tracker(s, params, 2)
+    trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    assert _cabi.last_launch_info()["streaming"] == (1 if gemm_path == "stream" else 0)
+    if gemm_path == "tensor":
+        os.environ.pop("NTM_B200_MODE", None)
+        for B, want in ((8, 0), (1024, 1)):
+            xb = torch.zeros(B, 2, s.input_dim, device="cuda")
+            trk(xb)
+            trk.cell.finish()
+            assert _cabi.last_launch_info()["streaming"] == want
