@@ -62,7 +62,7 @@ struct MemArgs {
   int oK, oE, oA, oSim, oWg, oWn, oSm, oX;   // shared-memory carve-up (floats)
   int WPC;                                   // warps sharing one 8-chunk column group in pass 2
   // TMA-ring kernel: stages of RPS memory rows, NS stages, NCH chunks per pass
-  int RPS, NS, NCH, RP;                      // RP: row phases of pass 2 (threads = RP * MC)
+  int RPS, NS, NCH, RP, SPS, rps_shift;      // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = SPS stages
   int oWp, oRaw, oBar, oRing;                // w_prev copy, raw parameter row, mbarriers, ring (floats)
   int l2_hints;
 };
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
 // stage in place and hands it to a bulk store.  Bytes in flight per CTA = the ring, independent of
 // registers and occupancy -- which is what an HBM-latency-bound stream needs.
 constexpr int TMA_NT = 256;
-constexpr int TMA_LAG = 2;    // a pass-2 stage is reloaded once the store issued TMA_LAG chunks ago has read it
+constexpr int TMA_NS = 8;     // ring stages
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
@@ -471,6 +471,15 @@ __device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t 
                  ::"l"(dst), "r"(s_u32(src)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
+__device__ __forceinline__ void bulk_store_nc(void* dst, const void* src, uint32_t bytes, uint64_t pol, bool hint) {
+  if (hint)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
+                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes), "l"(pol) : "memory");
+  else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int NKEEP>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NKEEP) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
@@ -488,12 +497,12 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 
 template <int R, int W, int CPL>
 __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a) {
-  constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32;
+  constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32, NS = TMA_NS;
   extern __shared__ float4 mem_smem4[];
   float* smem = reinterpret_cast<float*>(mem_smem4);
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N, M = a.M, M4 = a.M4, MC = a.MC, Npad = a.Npad, S = a.S;
-  const int RPS = a.RPS, NS = a.NS, NCH = a.NCH;
+  const int RPS = a.RPS, NCH = a.NCH;          // RPS: power of two >= 4 that divides N
   float* kS = smem + a.oK;
   float* eS = smem + a.oE;
   float* aS = smem + a.oA;
@@ -512,38 +521,38 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   const float* Mi = a.Min + (size_t)b * a.sMin;
   float* Mo = a.Mout + (size_t)b * a.sMout;
   float* cnb = a.cn + (size_t)b * M4;
-  const size_t stage_floats = (size_t)RPS * M;
+  const int stage_floats = RPS * M;
+  const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
   const bool hint = a.l2_hints != 0;
   // pass 1 brings the rows in and wants them to survive in L2 until pass 2 re-reads them; after that
   // re-read, and for the rewritten rows, the next use is a whole timestep (the other sequences) away
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
 
-  // chunk sequence number Q: 0..NCH-1 = pass 1, NCH..2*NCH-1 = pass 2; stage Q % NS, parity (Q / NS) & 1
+  // stage sequence number Q: 0..NCH-1 = pass 1, NCH..2*NCH-1 = pass 2; slot Q % NS, parity (Q / NS) & 1
   auto issue_load = [&](int Q) {
     const int j = Q < NCH ? Q : Q - NCH;
-    const int r0 = j * RPS;
-    const uint32_t bytes = (uint32_t)(min(RPS, N - r0) * M) * 4u;
-    uint64_t* fb = bars + (Q % NS);
-    mbar_expect_tx(fb, bytes);
-    bulk_load(ring + (size_t)(Q % NS) * stage_floats, Mi + (size_t)r0 * M, bytes, fb, Q < NCH ? pol_keep : pol_drop, hint);
+    uint64_t* fb = bars + (Q & (NS - 1));
+    mbar_expect_tx(fb, stage_bytes);
+    bulk_load(ring + (Q & (NS - 1)) * stage_floats, Mi + (size_t)j * stage_floats, stage_bytes, fb,
+              Q < NCH ? pol_keep : pol_drop, hint);
   };
 
   if (tid == 0) {
     for (int s2 = 0; s2 <= NS; ++s2) mbar_init_(bars + s2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     fence_async_smem();
+  }
+  __syncthreads();            // barrier inits visible to every thread before anyone polls
+  if (tid == 0) {
     mbar_expect_tx(rawbar, (uint32_t)a.PO4 * 4u);
     bulk_load(raw, a.mc + (size_t)b * a.PO4, (uint32_t)a.PO4 * 4u, rawbar, pol_drop, hint);
     for (int Q = 0; Q < NS && Q < 2 * NCH; ++Q) issue_load(Q);
   }
   {   // weightings entering the step -> shared memory (consumed after pass 1)
     const float* wprev = a.w_in + (size_t)b * a.sw_in;
-    for (int i = tid; i < H * N; i += NT) {
-      const int h = i / N, n = i - h * N;
-      wprevS[h * Npad + n] = __ldcg(wprev + i);
-    }
+    for (int h = 0; h < H; ++h)
+      for (int n = tid; n < N; n += NT) wprevS[h * Npad + n] = __ldcg(wprev + h * N + n);
   }
-  __syncthreads();            // barrier inits visible to every thread before anyone polls
   mbar_wait_(rawbar, 0);
 
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
@@ -553,19 +562,18 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     float ss[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) ss[h] = 0.0f;
-    for (int d = tid; d < M4; d += NT) {
-      const bool in = d < M;
-      const float cnd = in ? __ldcg(cnb + d) : 0.0f;
+    for (int d = tid; d < M; d += NT) {
+      const float cnd = __ldcg(cnb + d);
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        const float kv = in ? tanh_f(raw[h * M + d]) : 0.0f;
+        const float kv = tanh_f(raw[h * M + d]);
         kS[h * M4 + d] = kv * cnd;
         ss[h] = fmaf(kv, kv, ss[h]);
       }
 #pragma unroll
       for (int h = 0; h < W; ++h) {
-        eS[h * M4 + d] = in ? sigmoid_f(raw[offE + h * M + d]) : 0.0f;
-        aS[h * M4 + d] = in ? tanh_f(raw[offA + h * M + d]) : 0.0f;
+        eS[h * M4 + d] = sigmoid_f(raw[offE + h * M + d]);
+        aS[h * M4 + d] = tanh_f(raw[offA + h * M + d]);
       }
     }
 #pragma unroll
@@ -605,7 +613,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   }
   __syncthreads();
 
-  // ---- pass 1: a warp owns chunk q = warp, warp + NWARP, ...; keys in registers ----
+  // ---- pass 1: a warp owns stage q = warp, warp + NWARP, ...; keys in registers; four rows at a time ----
   {
     float4 kr[H][CPL];
 #pragma unroll
@@ -615,12 +623,12 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         const int c = lane + 32 * j;
         kr[h][j] = c < MC ? *reinterpret_cast<const float4*>(kS + h * M4 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    const int vi = lane / H, vh = lane - vi * H;   // value index of the transposing reduction -> (row, head)
     for (int q = warp; q < NCH; q += NWARP) {
-      const int st = q % NS;
-      mbar_wait_(bars + st, (uint32_t)(q / NS) & 1u);
-      const float* sp = ring + (size_t)st * stage_floats;
-      const int r0 = q * RPS, nr = min(RPS, N - r0);
-      for (int g0 = 0; g0 < nr; g0 += RB) {
+      mbar_wait_(bars + (q & (NS - 1)), (uint32_t)(q / NS) & 1u);
+      const float* sp = ring + (q & (NS - 1)) * stage_floats + 4 * lane;
+      float* simq = simS + vh * Npad + q * RPS + vi;
+      for (int g0 = 0; g0 < RPS; g0 += RB, sp += RB * M) {
         float acc[RB][H];
 #pragma unroll
         for (int i = 0; i < RB; ++i)
@@ -628,12 +636,10 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-          const int c = lane + 32 * j;
-          if (c < MC) {
+          if (lane + 32 * j < MC) {
             float4 m4[RB];
 #pragma unroll
-            for (int i = 0; i < RB; ++i)
-              m4[i] = *reinterpret_cast<const float4*>(sp + (size_t)min(g0 + i, nr - 1) * M + 4 * c);
+            for (int i = 0; i < RB; ++i) m4[i] = *reinterpret_cast<const float4*>(sp + i * M + 128 * j);
 #pragma unroll
             for (int i = 0; i < RB; ++i)
 #pragma unroll
@@ -645,6 +651,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
               }
           }
         }
+        // transposing reduction of the RB*H <= 32 values: lane L ends with the warp total of value L
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.0f;
@@ -662,10 +669,9 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
             v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        const int vi = lane / H, vh = lane - vi * H;
-        if (lane < RB * H && g0 + vi < nr) simS[vh * Npad + r0 + g0 + vi] = v[0];
+        if (lane < RB * H) simq[g0] = v[0];
       }
-      // this warp was the stage's only reader: refill it (next pass-1 chunk, or the head of pass 2)
+      // this warp was the stage's only reader: refill it (next pass-1 stage, or the head of pass 2)
       __syncwarp();
       if (lane == 0 && q + NS < 2 * NCH) issue_load(q + NS);
     }
@@ -757,11 +763,11 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   }
   __syncthreads();
 
-  // ---- pass 2: thread -> (16-byte column chunk c, row phase rp); the stage is updated in place and
-  //      handed to a bulk store ----
-  const int RP = a.RP;
+  // ---- pass 2: thread -> (16-byte column chunk c, quad slot rp); per iteration the CTA updates RP quads
+  //      of four consecutive rows (= SPS whole stages) in place and hands the stages to bulk stores ----
+  const int RP = a.RP, SPS = a.SPS;            // RP = NT / MC quads per iteration = SPS stages
   const bool worker = tid < RP * MC;
-  const int c = worker ? tid % MC : 0, rp = worker ? tid / MC : 0;
+  const int rp = worker ? tid / MC : 0, c = worker ? tid - rp * MC : 0;
   float4 racc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -773,56 +779,72 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
       e4[h] = *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c);
       a4[h] = *reinterpret_cast<const float4*>(aS + h * M4 + 4 * c);
     }
-    for (int j = 0; j < NCH; ++j) {
-      const int Q = NCH + j, st = Q % NS;
-      mbar_wait_(bars + st, (uint32_t)(Q / NS) & 1u);
-      float* sp = ring + (size_t)st * stage_floats;
-      const int r0 = j * RPS, nr = min(RPS, N - r0);
-      if (worker) {
-        for (int rl = rp; rl < nr; rl += RP) {
-          const int n = r0 + rl;
-          float4* mp = reinterpret_cast<float4*>(sp + (size_t)rl * M) + c;
-          const float4 m = *mp;
+    const int RS = 4 * RP;                       // rows per iteration
+    const int qshift = a.rps_shift;              // log2(RPS)
+    int it = 0;
+    for (int nb = 0; nb < N; nb += RS, ++it) {
+      const int n0 = nb + 4 * rp;                // this thread's quad
+      if (worker && n0 < N) {
+        const int j = n0 >> qshift, Q = NCH + j;
+        mbar_wait_(bars + (Q & (NS - 1)), (uint32_t)(Q / NS) & 1u);
+        float* mp = ring + (Q & (NS - 1)) * stage_floats + (n0 - (j << qshift)) * M + 4 * c;
+        float4 wv[H];                            // the four rows' weights of every head
+#pragma unroll
+        for (int h = 0; h < H; ++h) wv[h] = *reinterpret_cast<const float4*>(wnew + h * Npad + n0);
+        float4 m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const float4*>(mp + i * M);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          auto wsel = [&](int h) -> float { return i == 0 ? wv[h].x : (i == 1 ? wv[h].y : (i == 2 ? wv[h].z : wv[h].w)); };
           float4 mn;
           if constexpr (W == 1) {
-            const float ww = wnew[R * Npad + n];
-            mn.x = fmaf(ww, fmaf(-m.x, e4[0].x, a4[0].x), m.x);
-            mn.y = fmaf(ww, fmaf(-m.y, e4[0].y, a4[0].y), m.y);
-            mn.z = fmaf(ww, fmaf(-m.z, e4[0].z, a4[0].z), m.z);
-            mn.w = fmaf(ww, fmaf(-m.w, e4[0].w, a4[0].w), m.w);
+            // one write head: M' = M (1 - w e) + w a = M + w (a - M e)
+            const float ww = wsel(R);
+            mn.x = fmaf(ww, fmaf(-m[i].x, e4[0].x, a4[0].x), m[i].x);
+            mn.y = fmaf(ww, fmaf(-m[i].y, e4[0].y, a4[0].y), m[i].y);
+            mn.z = fmaf(ww, fmaf(-m[i].z, e4[0].z, a4[0].z), m[i].z);
+            mn.w = fmaf(ww, fmaf(-m[i].w, e4[0].w, a4[0].w), m[i].w);
           } else {
             float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int h = 0; h < W; ++h) {
-              const float ww = wnew[(R + h) * Npad + n];
+              const float ww = wsel(R + h);
               E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
               E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
               A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
               A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
             }
-            mn.x = fmaf(m.x, E.x, A.x); mn.y = fmaf(m.y, E.y, A.y);
-            mn.z = fmaf(m.z, E.z, A.z); mn.w = fmaf(m.w, E.w, A.w);
+            mn.x = fmaf(m[i].x, E.x, A.x); mn.y = fmaf(m[i].y, E.y, A.y);
+            mn.z = fmaf(m[i].z, E.z, A.z); mn.w = fmaf(m[i].w, E.w, A.w);
           }
-          const float4 mu = a.write_first ? mn : m;
+          const float4 mu = a.write_first ? mn : m[i];
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const float wr = wnew[r * Npad + n];
+            const float wr = wsel(r);
             racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
             racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
           }
           csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
           csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
-          *mp = mn;
+          *reinterpret_cast<float4*>(mp + i * M) = mn;
         }
       }
-      fence_async_smem();        // this thread's stage writes -> visible to the bulk store
+      fence_async_smem();        // this thread's stage writes -> visible to the bulk stores
       __syncthreads();
       if (tid == 0) {
-        bulk_store(Mo + (size_t)r0 * M, sp, (uint32_t)(nr * M) * 4u, pol_drop, hint);
-        if (j >= TMA_LAG) {      // the store of chunk j - LAG has read its stage: reload it
-          bulk_wait_read<TMA_LAG>();
-          const int Q2 = Q - TMA_LAG + NS;
-          if (Q2 < 2 * NCH) issue_load(Q2);
+        const int j0 = it * SPS;
+        for (int k = 0; k < SPS && j0 + k < NCH; ++k) {
+          const int Q = NCH + j0 + k;
+          bulk_store_nc(Mo + (size_t)(j0 + k) * stage_floats, ring + (Q & (NS - 1)) * stage_floats, stage_bytes, pol_drop, hint);
+        }
+        bulk_commit();
+        if (it >= 1) {           // the previous iteration's stores have read their stages: reload them
+          bulk_wait_read<1>();
+          for (int k = 0; k < SPS; ++k) {
+            const int Q2 = NCH + (it - 1) * SPS + k + NS;
+            if (Q2 < 2 * NCH) issue_load(Q2);
+          }
         }
       }
     }
@@ -830,27 +852,30 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   if (tid == 0) bulk_wait_all();
   __syncthreads();
 
-  // ---- finalize: partials over the row phases (fixed order) through the now idle ring ----
+  // ---- finalize: partials over the quad slots (fixed order) through the now idle ring ----
   {
     float* xch = ring;     // [RP][R+1][M4]
     if (worker) {
-      float* xw = xch + (size_t)rp * (R + 1) * M4;
+      float* xw = xch + rp * (R + 1) * M4 + 4 * c;
 #pragma unroll
-      for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(xw + r * M4 + 4 * c) = racc[r];
-      *reinterpret_cast<float4*>(xw + R * M4 + 4 * c) = csq;
+      for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(xw + r * M4) = racc[r];
+      *reinterpret_cast<float4*>(xw + R * M4) = csq;
     }
     __syncthreads();
     float* ar = a.act_read + (size_t)b * a.s_act;
     float* ro = a.read_out != nullptr ? a.read_out + (size_t)b * a.s_read : nullptr;
-    for (int i = tid; i < (R + 1) * M; i += NT) {
-      const int r = i / M, d = i - r * M;
-      float s = 0.0f;
-      for (int q = 0; q < RP; ++q) s += xch[((size_t)q * (R + 1) + r) * M4 + d];
-      if (r < R) {
-        ar[i] = s;
-        if (ro) ro[i] = s;
-      } else {
-        cnb[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+    const int xs = (R + 1) * M4;
+    for (int d = tid; d < M; d += NT) {
+#pragma unroll
+      for (int r = 0; r <= R; ++r) {
+        float s = 0.0f;
+        for (int q = 0; q < RP; ++q) s += xch[q * xs + r * M4 + d];
+        if (r < R) {
+          ar[r * M + d] = s;
+          if (ro) ro[r * M + d] = s;
+        } else {
+          cnb[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));   // tf.nn.l2_normalize over N, ops.py:147-150
+        }
       }
     }
   }
@@ -1063,6 +1088,21 @@ cudaError_t launch_tma(int R, int W, int CPL, const MemArgs& a, long long B, int
   }
   return cudaErrorInvalidValue;
 }
+// Rows per ring stage: the largest power of two >= 4 that divides N with a stage of at most 8 KiB, but
+// no more rows than one pass-2 iteration covers (4 * NT / MC); 0 = shape not covered.
+int tma_rp(int MC) {   // quads per pass-2 iteration: the largest power of two <= NT / MC
+  int rp = 1;
+  while (2 * rp * MC <= TMA_NT) rp *= 2;
+  return rp;
+}
+int tma_rps(int N, int M) {
+  if (M % 4 != 0 || M > 512) return 0;
+  const int rs = 4 * tma_rp(M / 4);
+  int best = 0;
+  for (int r = 4; r * M <= 2048 && r <= rs; r *= 2)
+    if (N % r == 0 && rs / r <= TMA_NS) best = r;
+  return best;
+}
 // 0 when the TMA-ring kernel does not cover the shape (then the generic register-streaming kernel runs)
 int tma_cpl(int H, int MC) {
   const int cpl = MC <= 32 ? 1 : (MC <= 64 ? 2 : (MC <= 128 ? 4 : 0));
@@ -1184,7 +1224,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     const int smem = 4 * o;
     // TMA-ring kernel (when it covers the shape): its own carve-up replaces the generic one
     int smem_tma = 0;
-    const int cpl = (getenv("NTM_B200_NO_TMA_RING") == nullptr) ? tma_cpl(H, MC) : 0;
+    const int cpl = (getenv("NTM_B200_NO_TMA_RING") == nullptr && tma_rps(N, M) > 0) ? tma_cpl(H, MC) : 0;
     if (cpl) {
       int o2 = 0;
       auto take2 = [&](int n) { int r = o2; o2 += round_up(n, 4); return r; };
@@ -1192,10 +1232,13 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       ma.oSim = take2(H * Npad); ma.oWg = take2(H * Npad); ma.oWn = take2(H * Npad); ma.oWp = take2(H * Npad);
       ma.oRaw = take2(PO4);
       ma.oSm = take2(4 * H + H * SMAX + (TMA_NT / 32) * H + 3 * H * std::max(1, (TMA_NT / 32) / H) + 8);
-      ma.NS = 8;
-      ma.RPS = std::min(N, std::max(1, 2048 / M));
-      ma.NCH = ceil_div(N, ma.RPS);
-      ma.RP = std::max(1, TMA_NT / MC);
+      ma.NS = TMA_NS;
+      ma.RPS = tma_rps(N, M);
+      ma.rps_shift = 0;
+      while ((1 << ma.rps_shift) < ma.RPS) ++ma.rps_shift;
+      ma.NCH = N / ma.RPS;
+      ma.RP = tma_rp(MC);
+      ma.SPS = 4 * ma.RP / ma.RPS;
       ma.oBar = take2(2 * (ma.NS + 1) + 2);
       o2 = round_up(o2, 32);                      // 128-byte aligned ring
       ma.oRing = o2;
