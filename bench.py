@@ -416,6 +416,7 @@ def main():
             "memory_kernel_ms_per_step": mem_launch_ms * T,
             "init_ms_per_step": sum(m["init"] for m in stream_ms) / n,
             "xproj_ms": sum(xp_ms) / len(xp_ms),
+            "mem_kernel_phase_ns": _cabi.stream_phase_ns(),
             "note": "streaming mode: memory streamed from HBM once per sequence-step (second pass from L2); "
                     "algorithmic bytes count 3 passes, so frac can exceed what the DRAM traffic alone implies",
         }

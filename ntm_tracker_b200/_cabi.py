@@ -79,6 +79,7 @@ SYMBOLS = {
     "ntm_b200_set_profiling": (C.c_int32, [C.c_int32]),
     "ntm_b200_last_kernel_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ntm_b200_last_stream_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "ntm_b200_stream_phase_ns": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "ntm_b200_phase_cycles": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "ntm_b200_last_launch_info": (C.c_int32, [C.POINTER(C.c_int32)]),
     "ntm_b200_launch_count": (C.c_int64, []),
@@ -134,3 +135,14 @@ def last_stream_ms():
     steps = C.c_int32(0)
     check(load().ntm_b200_last_stream_ms(buf, C.byref(steps)), "last_stream_ms")
     return {"controller": buf[0], "head_params": buf[1], "memory": buf[2], "init": buf[3], "steps": steps.value}
+
+
+def stream_phase_ns():
+    """Streaming mode, profiling enabled: mean ns per phase of the memory kernel's CTAs in the last launch."""
+    buf = (C.c_double * 9)()
+    n = C.c_int32(0)
+    check(load().ntm_b200_stream_phase_ns(buf, C.byref(n)), "stream_phase_ns")
+    keys = ("wait_params", "activations", "pass1", "addressing", "pass2", "store_drain", "finalize", "cta", "launch_span")
+    d = dict(zip(keys, list(buf)))
+    d["ctas"] = n.value
+    return d

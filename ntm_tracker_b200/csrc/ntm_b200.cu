@@ -635,6 +635,12 @@ int32_t ntm_b200_last_stream_ms(float* out4, int32_t* steps) {
   return NTM_B200_OK;
 }
 
+int32_t ntm_b200_stream_phase_ns(double* out9, int32_t* ctas) {
+  if (!out9 || !ctas) return NTM_B200_ERR_NULL_POINTER;
+  *ctas = stream_phase_ns(out9);
+  return NTM_B200_OK;
+}
+
 int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_ctas) {
   if (!workspace || !out) return NTM_B200_ERR_NULL_POINTER;
   if (max_ctas < 1 || max_ctas > 1024) return NTM_B200_ERR_BAD_SHAPE;

@@ -63,8 +63,11 @@ struct MemArgs {
   int WPC;                                   // warps sharing one 8-chunk column group in pass 2
   // TMA-ring kernel: stages of RPS memory rows, NS stages, NCH chunks per pass
   int RPS, NS, NCH, RP, SPS, rps_shift;      // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = SPS stages
-  int oWp, oRaw, oBar, oRing;                // w_prev copy, raw parameter row, mbarriers, ring (floats)
+  int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
+  int vec_out;                               // read-vector rows are 16-byte aligned
+  long long B;
   int l2_hints;
+  long long* prof;                           // [B][8] phase timestamps (globaltimer ns) of the last launch, or null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
 // stage in place and hands it to a bulk store.  Bytes in flight per CTA = the ring, independent of
 // registers and occupancy -- which is what an HBM-latency-bound stream needs.
 constexpr int TMA_NT = 256;
-constexpr int TMA_NS = 8;     // ring stages
+constexpr int TMA_NS = 4;     // ring stages (one stage = the rows of one pass-2 iteration, 16 KiB at M*RP = 1024)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
@@ -479,7 +482,20 @@ __device__ __forceinline__ void bulk_store_nc(void* dst, const void* src, uint32
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
                  ::"l"(dst), "r"(s_u32(src)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void st_global_hint(float* p, const float4 v, uint64_t pol, bool hint) {
+  if (hint)
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+  else
+    __stcg(reinterpret_cast<float4*>(p), v);
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MEM_PROF(slot) do { if (a.prof != nullptr && tid == 0) a.prof[(size_t)b * 8 + (slot)] = gtimer(); } while (0)
 template <int NKEEP>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NKEEP) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
@@ -500,10 +516,10 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32, NS = TMA_NS;
   extern __shared__ float4 mem_smem4[];
   float* smem = reinterpret_cast<float*>(mem_smem4);
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = a.N, M = a.M, M4 = a.M4, MC = a.MC, Npad = a.Npad, S = a.S;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, M = a.M, M4 = a.M4, MC = a.MC, Npad = a.Npad, S = a.S;   // here N % 4 == 0: Npad == N
   const int RPS = a.RPS, NCH = a.NCH;          // RPS: power of two >= 4 that divides N
-  float* kS = smem + a.oK;
+  float* kS = smem + a.oK;      // [H][M4]; after pass 1: partials of the quad slots rp >= 1
   float* eS = smem + a.oE;
   float* aS = smem + a.oA;
   float* simS = smem + a.oSim;
@@ -511,16 +527,14 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   float* wnew = smem + a.oWn;
   float* wprevS = smem + a.oWp;
   float* raw = smem + a.oRaw;
+  float* cnS = smem + a.oCn;
   float* sm = smem + a.oSm;
   float* ring = smem + a.oRing;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.oBar);   // full[NS], rawbar
-  uint64_t* rawbar = bars + NS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.oBar);   // full[NS], parbar
+  uint64_t* parbar = bars + NS;
   float* sBeta = sm, *sG = sm + H, *sGam = sm + 2 * H, *sSw = sm + 4 * H;
   float* sPart = sm + 4 * H + H * SMAX;
   float* sRed = sPart + NWARP * H;
-  const float* Mi = a.Min + (size_t)b * a.sMin;
-  float* Mo = a.Mout + (size_t)b * a.sMout;
-  float* cnb = a.cn + (size_t)b * M4;
   const int stage_floats = RPS * M;
   const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
   const bool hint = a.l2_hints != 0;
@@ -528,13 +542,29 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   // re-read, and for the rewritten rows, the next use is a whole timestep (the other sequences) away
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
 
-  // stage sequence number Q: 0..NCH-1 = pass 1, NCH..2*NCH-1 = pass 2; slot Q % NS, parity (Q / NS) & 1
-  auto issue_load = [&](int Q) {
+  // Persistent CTA: sequences b = blockIdx.x + si * gridDim.x.  The ring never drains between sequences:
+  // stage use Qg (global over this CTA's sequences; per sequence NCH pass-1 stages then NCH pass-2 stages)
+  // lives in slot Qg % NS with mbarrier parity (Qg / NS) & 1, and whoever releases use Qg issues the load
+  // of use Qg + NS into the same slot -- so the head of the next sequence streams in behind pass 2.
+  const int G = gridDim.x;
+  const int nseq = ((int)a.B - (int)blockIdx.x + G - 1) / G;
+  const int QPS = 2 * NCH, QT = nseq * QPS;
+  auto issue_load = [&](int Qg) {
+    const int si = Qg / QPS, Q = Qg - si * QPS;
     const int j = Q < NCH ? Q : Q - NCH;
-    uint64_t* fb = bars + (Q & (NS - 1));
+    const float* src = a.Min + (size_t)(blockIdx.x + si * G) * a.sMin + (size_t)j * stage_floats;
+    uint64_t* fb = bars + (Qg & (NS - 1));
     mbar_expect_tx(fb, stage_bytes);
-    bulk_load(ring + (Q & (NS - 1)) * stage_floats, Mi + (size_t)j * stage_floats, stage_bytes, fb,
-              Q < NCH ? pol_keep : pol_drop, hint);
+    bulk_load(ring + (Qg & (NS - 1)) * stage_floats, src, stage_bytes, fb, Q < NCH ? pol_keep : pol_drop, hint);
+  };
+  // head parameters, entering weightings and inverse column norms of sequence si -> shared memory
+  const uint32_t par_bytes = (uint32_t)(a.PO4 + H * N + M4) * 4u;
+  auto issue_params = [&](int si) {
+    const size_t bb = (size_t)(blockIdx.x + si * G);
+    mbar_expect_tx(parbar, par_bytes);
+    bulk_load(raw, a.mc + bb * a.PO4, (uint32_t)a.PO4 * 4u, parbar, pol_drop, hint);
+    bulk_load(wprevS, a.w_in + bb * a.sw_in, (uint32_t)(H * N) * 4u, parbar, pol_drop, hint);
+    bulk_load(cnS, a.cn + bb * M4, (uint32_t)M4 * 4u, parbar, pol_drop, hint);
   };
 
   if (tid == 0) {
@@ -543,341 +573,359 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     fence_async_smem();
   }
   __syncthreads();            // barrier inits visible to every thread before anyone polls
-  if (tid == 0) {
-    mbar_expect_tx(rawbar, (uint32_t)a.PO4 * 4u);
-    bulk_load(raw, a.mc + (size_t)b * a.PO4, (uint32_t)a.PO4 * 4u, rawbar, pol_drop, hint);
-    for (int Q = 0; Q < NS && Q < 2 * NCH; ++Q) issue_load(Q);
+  if (tid == 0 && nseq > 0) {
+    issue_params(0);
+    for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg);
   }
-  {   // weightings entering the step -> shared memory (consumed after pass 1)
-    const float* wprev = a.w_in + (size_t)b * a.sw_in;
-    for (int h = 0; h < H; ++h)
-      for (int n = tid; n < N; n += NT) wprevS[h * Npad + n] = __ldcg(wprev + h * N + n);
-  }
-  mbar_wait_(rawbar, 0);
 
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
             offE = offGam + H, offA = offE + M * W;
-  // ---- activations (ntm_cell.py:133-196) ----
-  {
-    float ss[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) ss[h] = 0.0f;
-    for (int d = tid; d < M; d += NT) {
-      const float cnd = __ldcg(cnb + d);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float kv = tanh_f(raw[h * M + d]);
-        kS[h * M4 + d] = kv * cnd;
-        ss[h] = fmaf(kv, kv, ss[h]);
-      }
-#pragma unroll
-      for (int h = 0; h < W; ++h) {
-        eS[h * M4 + d] = sigmoid_f(raw[offE + h * M + d]);
-        aS[h * M4 + d] = tanh_f(raw[offA + h * M + d]);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int h = 0; h < H; ++h) ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
-    }
-  }
-  if (tid < H) {
-    sBeta[tid] = softplus_f(raw[offBeta + tid]);
-    sG[tid] = sigmoid_f(raw[offG + tid]);
-    sGam[tid] = 1.0f + softplus_f(raw[offGam + tid]);
-    float* sp = sSw + tid * SMAX;
-    float mx = -INFINITY;
-    for (int i = 0; i < S; ++i) { sp[i] = raw[offS + tid * S + i]; mx = fmaxf(mx, sp[i]); }
-    float sum = 0.0f;
-    for (int i = 0; i < S; ++i) { sp[i] = exp_f(sp[i] - mx); sum += sp[i]; }
-    const float rsum = __frcp_rn(sum);
-    for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
-  }
-  if (tid == NT - 1) {   // output projection + softmax (ntm_cell.py:220-221)
-    const size_t o = ((size_t)b * a.T + a.t) * a.O;
-    float mx = -INFINITY;
-    for (int i = 0; i < a.O; ++i) mx = fmaxf(mx, raw[a.P + i]);
-    float sum = 0.0f;
-    for (int i = 0; i < a.O; ++i) sum += exp_f(raw[a.P + i] - mx);
-    const float rsum = __frcp_rn(sum);
-    for (int i = 0; i < a.O; ++i) {
-      const float lg = raw[a.P + i];
-      a.logits[o + i] = lg;
-      if (a.outputs) a.outputs[o + i] = exp_f(lg - mx) * rsum;
-    }
-  }
-  __syncthreads();
-
-  // ---- pass 1: a warp owns stage q = warp, warp + NWARP, ...; keys in registers; four rows at a time ----
-  {
-    float4 kr[H][CPL];
-#pragma unroll
-    for (int h = 0; h < H; ++h)
-#pragma unroll
-      for (int j = 0; j < CPL; ++j) {
-        const int c = lane + 32 * j;
-        kr[h][j] = c < MC ? *reinterpret_cast<const float4*>(kS + h * M4 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    const int vi = lane / H, vh = lane - vi * H;   // value index of the transposing reduction -> (row, head)
-    for (int q = warp; q < NCH; q += NWARP) {
-      mbar_wait_(bars + (q & (NS - 1)), (uint32_t)(q / NS) & 1u);
-      const float* sp = ring + (q & (NS - 1)) * stage_floats + 4 * lane;
-      float* simq = simS + vh * Npad + q * RPS + vi;
-      for (int g0 = 0; g0 < RPS; g0 += RB, sp += RB * M) {
-        float acc[RB][H];
-#pragma unroll
-        for (int i = 0; i < RB; ++i)
-#pragma unroll
-          for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          if (lane + 32 * j < MC) {
-            float4 m4[RB];
-#pragma unroll
-            for (int i = 0; i < RB; ++i) m4[i] = *reinterpret_cast<const float4*>(sp + i * M + 128 * j);
-#pragma unroll
-            for (int i = 0; i < RB; ++i)
-#pragma unroll
-              for (int h = 0; h < H; ++h) {
-                acc[i][h] = fmaf(m4[i].x, kr[h][j].x, acc[i][h]);
-                acc[i][h] = fmaf(m4[i].y, kr[h][j].y, acc[i][h]);
-                acc[i][h] = fmaf(m4[i].z, kr[h][j].z, acc[i][h]);
-                acc[i][h] = fmaf(m4[i].w, kr[h][j].w, acc[i][h]);
-              }
-          }
-        }
-        // transposing reduction of the RB*H <= 32 values: lane L ends with the warp total of value L
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < RB; ++i)
-#pragma unroll
-          for (int h = 0; h < H; ++h) v[i * H + h] = acc[i][h];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const bool up = (lane & o) != 0;
-#pragma unroll
-          for (int j = 0; j < o; ++j) {
-            const float send = up ? v[j] : v[j + o];
-            const float keep = up ? v[j + o] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        }
-        if (lane < RB * H) simq[g0] = v[0];
-      }
-      // this warp was the stage's only reader: refill it (next pass-1 stage, or the head of pass 2)
-      __syncwarp();
-      if (lane == 0 && q + NS < 2 * NCH) issue_load(q + NS);
-    }
-  }
-  __syncthreads();
-
-  // ---- addressing (ntm_cell.py:140-176), same as mem_step_kernel but w_prev from shared memory ----
-  {
-    constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
-    constexpr bool multi = (NWARP / H) > 0;
-    const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
-    const int hstep = multi ? H : NWARP;
-    float* wout = a.w_out + (size_t)b * a.sw_out;
-    for (int h = multi ? hgrp : warp; h < H; h += hstep) {
-      float* sh = simS + h * Npad;
-      float* gh = wg + h * Npad;
-      float* red = sRed + h * 3 * WPH;
-      const int nstep = 32 * WPH;
-      const int n0 = 32 * sub + lane;
-      auto head_bar = [&]() {
-        if (WPH > 1) asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(32 * WPH) : "memory");
-        else __syncwarp();
-      };
-      const float gate = sG[h], gamma = sGam[h];
-      float kn = 0.0f;
-      for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
-      const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));
-      const float beta = sBeta[h];
-      float mx = -INFINITY;
-      for (int n = n0; n < N; n += nstep) {
-        const float x = sh[n] * rs * beta;
-        sh[n] = x;
-        mx = fmaxf(mx, x);
-      }
-      mx = warp_max(mx);
-      if (WPH > 1) {
-        if (lane == 0) red[sub] = mx;
-        head_bar();
-        mx = red[0];
-#pragma unroll
-        for (int i = 1; i < WPH; ++i) mx = fmaxf(mx, red[i]);
-      }
-      float sum = 0.0f;
-      for (int n = n0; n < N; n += nstep) {
-        const float e = exp_f(sh[n] - mx);
-        sh[n] = e;
-        sum += e;
-      }
-      sum = warp_sum(sum);
-      if (WPH > 1) {
-        if (lane == 0) red[WPH + sub] = sum;
-        head_bar();
-        sum = red[WPH];
-#pragma unroll
-        for (int i = 1; i < WPH; ++i) sum += red[WPH + i];
-      }
-      for (int n = n0; n < N; n += nstep) {
-        const float wc = sh[n] / sum;
-        gh[n] = wc * gate + wprevS[h * Npad + n] * (1.0f - gate);
-      }
-      head_bar();
-      float psum = 0.0f;
-      for (int n = n0; n < N; n += nstep) {
-        float conv = 0.0f;
-        for (int s = 0; s < S; ++s) {
-          int idx = n + a.shift0 + s;
-          idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
-          conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
-        }
-        const float pw = exp2f(gamma * log2f(conv));
-        sh[n] = pw;
-        psum += pw;
-      }
-      psum = warp_sum(psum);
-      if (WPH > 1) {
-        if (lane == 0) red[2 * WPH + sub] = psum;
-        head_bar();
-        psum = red[2 * WPH];
-#pragma unroll
-        for (int i = 1; i < WPH; ++i) psum += red[2 * WPH + i];
-      }
-      const float den = psum + 1e-3f;
-      for (int n = n0; n < N; n += nstep) {
-        const float wv = sh[n] / den;
-        wnew[h * Npad + n] = wv;
-        wout[h * N + n] = wv;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- pass 2: thread -> (16-byte column chunk c, quad slot rp); per iteration the CTA updates RP quads
-  //      of four consecutive rows (= SPS whole stages) in place and hands the stages to bulk stores ----
-  const int RP = a.RP, SPS = a.SPS;            // RP = NT / MC quads per iteration = SPS stages
+  const int RP = a.RP;                         // pass 2: RP quads of 4 rows per iteration = one stage
   const bool worker = tid < RP * MC;
   const int rp = worker ? tid / MC : 0, c = worker ? tid - rp * MC : 0;
-  float4 racc[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);
-  {
-    float4 e4[W], a4[W];
-#pragma unroll
-    for (int h = 0; h < W; ++h) {
-      e4[h] = *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c);
-      a4[h] = *reinterpret_cast<const float4*>(aS + h * M4 + 4 * c);
-    }
-    const int RS = 4 * RP;                       // rows per iteration
-    const int qshift = a.rps_shift;              // log2(RPS)
-    int it = 0;
-    for (int nb = 0; nb < N; nb += RS, ++it) {
-      const int n0 = nb + 4 * rp;                // this thread's quad
-      if (worker && n0 < N) {
-        const int j = n0 >> qshift, Q = NCH + j;
-        mbar_wait_(bars + (Q & (NS - 1)), (uint32_t)(Q / NS) & 1u);
-        float* mp = ring + (Q & (NS - 1)) * stage_floats + (n0 - (j << qshift)) * M + 4 * c;
-        float4 wv[H];                            // the four rows' weights of every head
-#pragma unroll
-        for (int h = 0; h < H; ++h) wv[h] = *reinterpret_cast<const float4*>(wnew + h * Npad + n0);
-        float4 m[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const float4*>(mp + i * M);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          auto wsel = [&](int h) -> float { return i == 0 ? wv[h].x : (i == 1 ? wv[h].y : (i == 2 ? wv[h].z : wv[h].w)); };
-          float4 mn;
-          if constexpr (W == 1) {
-            // one write head: M' = M (1 - w e) + w a = M + w (a - M e)
-            const float ww = wsel(R);
-            mn.x = fmaf(ww, fmaf(-m[i].x, e4[0].x, a4[0].x), m[i].x);
-            mn.y = fmaf(ww, fmaf(-m[i].y, e4[0].y, a4[0].y), m[i].y);
-            mn.z = fmaf(ww, fmaf(-m[i].z, e4[0].z, a4[0].z), m[i].z);
-            mn.w = fmaf(ww, fmaf(-m[i].w, e4[0].w, a4[0].w), m[i].w);
-          } else {
-            float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int h = 0; h < W; ++h) {
-              const float ww = wsel(R + h);
-              E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
-              E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
-              A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
-              A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
-            }
-            mn.x = fmaf(m[i].x, E.x, A.x); mn.y = fmaf(m[i].y, E.y, A.y);
-            mn.z = fmaf(m[i].z, E.z, A.z); mn.w = fmaf(m[i].w, E.w, A.w);
-          }
-          const float4 mu = a.write_first ? mn : m[i];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float wr = wsel(r);
-            racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
-            racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
-          }
-          csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
-          csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
-          *reinterpret_cast<float4*>(mp + i * M) = mn;
-        }
-      }
-      fence_async_smem();        // this thread's stage writes -> visible to the bulk stores
-      __syncthreads();
-      if (tid == 0) {
-        const int j0 = it * SPS;
-        for (int k = 0; k < SPS && j0 + k < NCH; ++k) {
-          const int Q = NCH + j0 + k;
-          bulk_store_nc(Mo + (size_t)(j0 + k) * stage_floats, ring + (Q & (NS - 1)) * stage_floats, stage_bytes, pol_drop, hint);
-        }
-        bulk_commit();
-        if (it >= 1) {           // the previous iteration's stores have read their stages: reload them
-          bulk_wait_read<1>();
-          for (int k = 0; k < SPS; ++k) {
-            const int Q2 = NCH + (it - 1) * SPS + k + NS;
-            if (Q2 < 2 * NCH) issue_load(Q2);
-          }
-        }
-      }
-    }
-  }
-  if (tid == 0) bulk_wait_all();
-  __syncthreads();
+  const int vi = lane / H, vh = lane - vi * H;   // value index of the transposing reduction -> (row, head)
 
-  // ---- finalize: partials over the quad slots (fixed order) through the now idle ring ----
-  {
-    float* xch = ring;     // [RP][R+1][M4]
-    if (worker) {
-      float* xw = xch + rp * (R + 1) * M4 + 4 * c;
+  for (int si = 0; si < nseq; ++si) {
+    const int b = blockIdx.x + si * G;
+    const int Qb = si * QPS;
+    float* Mo = a.Mout + (size_t)b * a.sMout;
+    MEM_PROF(0);
+    mbar_wait_(parbar, (uint32_t)si & 1u);
+    MEM_PROF(1);
+
+    // ---- activations (ntm_cell.py:133-196) ----
+    {
+      float ss[H];
 #pragma unroll
-      for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(xw + r * M4) = racc[r];
-      *reinterpret_cast<float4*>(xw + R * M4) = csq;
+      for (int h = 0; h < H; ++h) ss[h] = 0.0f;
+      for (int d = tid; d < M; d += NT) {
+        const float cnd = cnS[d];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float kv = tanh_f(raw[h * M + d]);
+          kS[h * M4 + d] = kv * cnd;
+          ss[h] = fmaf(kv, kv, ss[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < W; ++h) {
+          eS[h * M4 + d] = sigmoid_f(raw[offE + h * M + d]);
+          aS[h * M4 + d] = tanh_f(raw[offA + h * M + d]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
+      }
+    }
+    if (tid < H) {
+      sBeta[tid] = softplus_f(raw[offBeta + tid]);
+      sG[tid] = sigmoid_f(raw[offG + tid]);
+      sGam[tid] = 1.0f + softplus_f(raw[offGam + tid]);
+      float* sp = sSw + tid * SMAX;
+      float mx = -INFINITY;
+      for (int i = 0; i < S; ++i) { sp[i] = raw[offS + tid * S + i]; mx = fmaxf(mx, sp[i]); }
+      float sum = 0.0f;
+      for (int i = 0; i < S; ++i) { sp[i] = exp_f(sp[i] - mx); sum += sp[i]; }
+      const float rsum = __frcp_rn(sum);
+      for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
+    }
+    if (tid == NT - 1) {   // output projection + softmax (ntm_cell.py:220-221)
+      const size_t o = ((size_t)b * a.T + a.t) * a.O;
+      float mx = -INFINITY;
+      for (int i = 0; i < a.O; ++i) mx = fmaxf(mx, raw[a.P + i]);
+      float sum = 0.0f;
+      for (int i = 0; i < a.O; ++i) sum += exp_f(raw[a.P + i] - mx);
+      const float rsum = __frcp_rn(sum);
+      for (int i = 0; i < a.O; ++i) {
+        const float lg = raw[a.P + i];
+        a.logits[o + i] = lg;
+        if (a.outputs) a.outputs[o + i] = exp_f(lg - mx) * rsum;
+      }
     }
     __syncthreads();
-    float* ar = a.act_read + (size_t)b * a.s_act;
-    float* ro = a.read_out != nullptr ? a.read_out + (size_t)b * a.s_read : nullptr;
-    const int xs = (R + 1) * M4;
-    for (int d = tid; d < M; d += NT) {
+    MEM_PROF(2);
+
+    // ---- pass 1: a warp owns stage q = warp, warp + NWARP, ...; keys in registers; four rows at a time ----
+    {
+      float4 kr[H][CPL];
 #pragma unroll
-      for (int r = 0; r <= R; ++r) {
-        float s = 0.0f;
-        for (int q = 0; q < RP; ++q) s += xch[q * xs + r * M4 + d];
-        if (r < R) {
-          ar[r * M + d] = s;
-          if (ro) ro[r * M + d] = s;
-        } else {
-          cnb[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));   // tf.nn.l2_normalize over N, ops.py:147-150
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int cc = lane + 32 * j;
+          kr[h][j] = cc < MC ? *reinterpret_cast<const float4*>(kS + h * M4 + 4 * cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      // NWARP / NS warps share a stage (a warp may only wait on the use that directly follows the one it
+      // consumed last -- an mbarrier cannot be waited on two phases ahead): team = slot, member = quad parity
+      constexpr int WPS = NWARP / NS;
+      const int team = warp % NS, member = warp / NS;
+      for (int q = team; q < NCH; q += NS) {
+        const int Qg = Qb + q;
+        mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
+        const float* sp = ring + (Qg & (NS - 1)) * stage_floats + 4 * lane + member * RB * M;
+        float* simq = simS + vh * Npad + q * RPS + vi;
+        for (int g0 = member * RB; g0 < RPS; g0 += WPS * RB, sp += WPS * RB * M) {
+          float acc[RB][H];
+#pragma unroll
+          for (int i = 0; i < RB; ++i)
+#pragma unroll
+            for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            if (lane + 32 * j < MC) {
+              float4 m4[RB];
+#pragma unroll
+              for (int i = 0; i < RB; ++i) m4[i] = *reinterpret_cast<const float4*>(sp + i * M + 128 * j);
+#pragma unroll
+              for (int i = 0; i < RB; ++i)
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                  acc[i][h] = fmaf(m4[i].x, kr[h][j].x, acc[i][h]);
+                  acc[i][h] = fmaf(m4[i].y, kr[h][j].y, acc[i][h]);
+                  acc[i][h] = fmaf(m4[i].z, kr[h][j].z, acc[i][h]);
+                  acc[i][h] = fmaf(m4[i].w, kr[h][j].w, acc[i][h]);
+                }
+            }
+          }
+          // transposing reduction of the RB*H <= 32 values: lane L ends with the warp total of value L
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+#pragma unroll
+          for (int i = 0; i < RB; ++i)
+#pragma unroll
+            for (int h = 0; h < H; ++h) v[i * H + h] = acc[i][h];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const float send = up ? v[j] : v[j + o];
+              const float keep = up ? v[j + o] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          if (lane < RB * H) simq[g0] = v[0];
+        }
+        // the team were the stage's only readers: once all of them are done, refill the slot with use Qg + NS
+        asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPS) : "memory");
+        if (member == 0 && lane == 0 && Qg + NS < QT) issue_load(Qg + NS);
+      }
+    }
+    __syncthreads();
+    MEM_PROF(3);
+
+    // ---- addressing (ntm_cell.py:140-176), as in mem_step_kernel but w_prev from shared memory ----
+    {
+      constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
+      constexpr bool multi = (NWARP / H) > 0;
+      const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
+      const int hstep = multi ? H : NWARP;
+      float* wout = a.w_out + (size_t)b * a.sw_out;
+      for (int h = multi ? hgrp : warp; h < H; h += hstep) {
+        float* sh = simS + h * Npad;
+        float* gh = wg + h * Npad;
+        float* red = sRed + h * 3 * WPH;
+        const int nstep = 32 * WPH;
+        const int n0 = 32 * sub + lane;
+        auto head_bar = [&]() {
+          if (WPH > 1) asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"(32 * WPH) : "memory");
+          else __syncwarp();
+        };
+        const float gate = sG[h], gamma = sGam[h];
+        float kn = 0.0f;
+        for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+        const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));
+        const float beta = sBeta[h];
+        float mx = -INFINITY;
+        for (int n = n0; n < N; n += nstep) {
+          const float x = sh[n] * rs * beta;
+          sh[n] = x;
+          mx = fmaxf(mx, x);
+        }
+        mx = warp_max(mx);
+        if (WPH > 1) {
+          if (lane == 0) red[sub] = mx;
+          head_bar();
+          mx = red[0];
+#pragma unroll
+          for (int i = 1; i < WPH; ++i) mx = fmaxf(mx, red[i]);
+        }
+        float sum = 0.0f;
+        for (int n = n0; n < N; n += nstep) {
+          const float e = exp_f(sh[n] - mx);
+          sh[n] = e;
+          sum += e;
+        }
+        sum = warp_sum(sum);
+        if (WPH > 1) {
+          if (lane == 0) red[WPH + sub] = sum;
+          head_bar();
+          sum = red[WPH];
+#pragma unroll
+          for (int i = 1; i < WPH; ++i) sum += red[WPH + i];
+        }
+        for (int n = n0; n < N; n += nstep) {
+          const float wc = sh[n] / sum;
+          gh[n] = wc * gate + wprevS[h * N + n] * (1.0f - gate);
+        }
+        head_bar();
+        float psum = 0.0f;
+        for (int n = n0; n < N; n += nstep) {
+          float conv = 0.0f;
+          for (int s = 0; s < S; ++s) {
+            int idx = n + a.shift0 + s;
+            idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+            conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
+          }
+          const float pw = exp2f(gamma * log2f(conv));
+          sh[n] = pw;
+          psum += pw;
+        }
+        psum = warp_sum(psum);
+        if (WPH > 1) {
+          if (lane == 0) red[2 * WPH + sub] = psum;
+          head_bar();
+          psum = red[2 * WPH];
+#pragma unroll
+          for (int i = 1; i < WPH; ++i) psum += red[2 * WPH + i];
+        }
+        const float den = psum + 1e-3f;
+        for (int n = n0; n < N; n += nstep) {
+          const float wv = sh[n] / den;
+          wnew[h * Npad + n] = wv;
+          wout[h * N + n] = wv;
         }
       }
     }
+    __syncthreads();
+    MEM_PROF(4);
+    // raw / wprevS / cnS are dead now: the next sequence's parameters stream in behind pass 2
+    if (tid == 0 && si + 1 < nseq) issue_params(si + 1);
+
+    // ---- pass 2: thread -> (16-byte column chunk c, quad slot rp); per iteration the CTA reads RP quads
+    //      of four consecutive rows (= SPS whole stages) from the ring and writes M' straight to HBM ----
+    float4 racc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+      float4 e4[W], a4[W];
+#pragma unroll
+      for (int h = 0; h < W; ++h) {
+        e4[h] = *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c);
+        a4[h] = *reinterpret_cast<const float4*>(aS + h * M4 + 4 * c);
+      }
+      const int RS = 4 * RP;                       // rows per iteration = rows per stage
+      int it = 0;
+      for (int nb = 0; nb < N; nb += RS, ++it) {
+        const int n0 = nb + 4 * rp;                // this thread's quad
+        if (worker && n0 < N) {
+          const int Qg = Qb + NCH + it;
+          mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
+          const float* mp = ring + (Qg & (NS - 1)) * stage_floats + 4 * rp * M + 4 * c;
+          float* gp = Mo + (size_t)n0 * M + 4 * c;
+          float4 wv[H];                            // the four rows' weights of every head
+#pragma unroll
+          for (int h = 0; h < H; ++h) wv[h] = *reinterpret_cast<const float4*>(wnew + h * Npad + n0);
+          float4 m[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const float4*>(mp + i * M);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            auto wsel = [&](int h) -> float { return i == 0 ? wv[h].x : (i == 1 ? wv[h].y : (i == 2 ? wv[h].z : wv[h].w)); };
+            float4 mn;
+            if constexpr (W == 1) {
+              // one write head: M' = M (1 - w e) + w a = M + w (a - M e)
+              const float ww = wsel(R);
+              mn.x = fmaf(ww, fmaf(-m[i].x, e4[0].x, a4[0].x), m[i].x);
+              mn.y = fmaf(ww, fmaf(-m[i].y, e4[0].y, a4[0].y), m[i].y);
+              mn.z = fmaf(ww, fmaf(-m[i].z, e4[0].z, a4[0].z), m[i].z);
+              mn.w = fmaf(ww, fmaf(-m[i].w, e4[0].w, a4[0].w), m[i].w);
+            } else {
+              float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int h = 0; h < W; ++h) {
+                const float ww = wsel(R + h);
+                E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
+                E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
+                A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
+                A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
+              }
+              mn.x = fmaf(m[i].x, E.x, A.x); mn.y = fmaf(m[i].y, E.y, A.y);
+              mn.z = fmaf(m[i].z, E.z, A.z); mn.w = fmaf(m[i].w, E.w, A.w);
+            }
+            const float4 mu = a.write_first ? mn : m[i];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float wr = wsel(r);
+              racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
+              racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
+            }
+            csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
+            csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
+            st_global_hint(gp + (size_t)i * M, mn, pol_drop, hint);
+          }
+        }
+        __syncthreads();         // every reader of this iteration's stage is done
+        // one bulk copy costs its issuing thread ~240 ns (tools/tma_probe.cu): rotate the issuer over the
+        // warps so that no warp pays it twice in a row
+        if (tid == ((it & (NWARP - 1)) << 5)) {
+          const int Qn = Qb + NCH + it + NS;
+          if (Qn < QT) issue_load(Qn);
+        }
+      }
+    }
+    MEM_PROF(5);
+
+    // ---- finalize: quad slots rp >= 1 park their partials in the (dead) key buffer; slot 0 adds them in
+    //      fixed order and writes the read vector and the new inverse column norms ----
+    {
+      float* xch = kS;     // [RP-1][R+1][M4]
+      if (worker && rp > 0) {
+        float* xw = xch + (rp - 1) * (R + 1) * M4 + 4 * c;
+#pragma unroll
+        for (int r = 0; r < R; ++r) *reinterpret_cast<float4*>(xw + r * M4) = racc[r];
+        *reinterpret_cast<float4*>(xw + R * M4) = csq;
+      }
+      __syncthreads();
+      MEM_PROF(6);
+      if (worker && rp == 0) {
+        for (int q = 1; q < RP; ++q) {
+          const float* xr = xch + (q - 1) * (R + 1) * M4 + 4 * c;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 t = *reinterpret_cast<const float4*>(xr + r * M4);
+            racc[r].x += t.x; racc[r].y += t.y; racc[r].z += t.z; racc[r].w += t.w;
+          }
+          const float4 t = *reinterpret_cast<const float4*>(xr + R * M4);
+          csq.x += t.x; csq.y += t.y; csq.z += t.z; csq.w += t.w;
+        }
+        float* ar = a.act_read + (size_t)b * a.s_act + 4 * c;
+        float* ro = a.read_out != nullptr ? a.read_out + (size_t)b * a.s_read + 4 * c : nullptr;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (a.vec_out) {
+            *reinterpret_cast<float4*>(ar + r * M) = racc[r];
+            if (ro) *reinterpret_cast<float4*>(ro + r * M) = racc[r];
+          } else {
+            ar[r * M] = racc[r].x; ar[r * M + 1] = racc[r].y; ar[r * M + 2] = racc[r].z; ar[r * M + 3] = racc[r].w;
+            if (ro) { ro[r * M] = racc[r].x; ro[r * M + 1] = racc[r].y; ro[r * M + 2] = racc[r].z; ro[r * M + 3] = racc[r].w; }
+          }
+        }
+        float4 cn4;   // tf.nn.l2_normalize over N, ops.py:147-150
+        cn4.x = 1.0f / sqrtf(fmaxf(csq.x, 1e-12f)); cn4.y = 1.0f / sqrtf(fmaxf(csq.y, 1e-12f));
+        cn4.z = 1.0f / sqrtf(fmaxf(csq.z, 1e-12f)); cn4.w = 1.0f / sqrtf(fmaxf(csq.w, 1e-12f));
+        *reinterpret_cast<float4*>(a.cn + (size_t)b * M4 + 4 * c) = cn4;
+      }
+      __syncthreads();           // kS is rewritten by the next sequence's activations
+    }
+    MEM_PROF(7);
   }
 }
 
@@ -1056,8 +1104,15 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
       if (e != cudaSuccess) return e;
       configured = smem;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_tma_kernel<R, W, CPL>, TMA_NT, smem);
+      if (g_mem_occ < 1) g_mem_occ = 1;
     }
-    mem_step_tma_kernel<R, W, CPL><<<(unsigned)B, TMA_NT, smem, stream>>>(a);
+    int nsm = B200_SMS;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = g_mem_occ;
+    if (const char* ev = getenv("NTM_B200_MEM_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(ev)));
+    const long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
+    mem_step_tma_kernel<R, W, CPL><<<(unsigned)grid, TMA_NT, smem, stream>>>(a);
     return cudaGetLastError();
   }
 }
@@ -1088,8 +1143,8 @@ cudaError_t launch_tma(int R, int W, int CPL, const MemArgs& a, long long B, int
   }
   return cudaErrorInvalidValue;
 }
-// Rows per ring stage: the largest power of two >= 4 that divides N with a stage of at most 8 KiB, but
-// no more rows than one pass-2 iteration covers (4 * NT / MC); 0 = shape not covered.
+// Rows per ring stage = the rows one pass-2 iteration covers (4 * RP; 16 KiB when MC divides 256);
+// must divide N.  0 = shape not covered (the generic kernel runs).
 int tma_rp(int MC) {   // quads per pass-2 iteration: the largest power of two <= NT / MC
   int rp = 1;
   while (2 * rp * MC <= TMA_NT) rp *= 2;
@@ -1097,11 +1152,8 @@ int tma_rp(int MC) {   // quads per pass-2 iteration: the largest power of two <
 }
 int tma_rps(int N, int M) {
   if (M % 4 != 0 || M > 512) return 0;
-  const int rs = 4 * tma_rp(M / 4);
-  int best = 0;
-  for (int r = 4; r * M <= 2048 && r <= rs; r *= 2)
-    if (N % r == 0 && rs / r <= TMA_NS) best = r;
-  return best;
+  const int rs = 4 * tma_rp(M / 4);            // rows of one pass-2 iteration
+  return (N % rs == 0) ? rs : 0;
 }
 // 0 when the TMA-ring kernel does not cover the shape (then the generic register-streaming kernel runs)
 int tma_cpl(int H, int MC) {
@@ -1111,6 +1163,8 @@ int tma_cpl(int H, int MC) {
 }
 
 thread_local std::vector<cudaEvent_t> g_sev;
+thread_local long long* g_prof_ptr = nullptr;
+thread_local long long g_prof_B = 0;
 thread_local int g_sev_steps = 0;
 
 }  // namespace
@@ -1156,6 +1210,7 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
   ws->off_partA = take(4ll * ksmax * ws->slabA);
   ws->off_mc = take(4ll * ws->slabC);
   ws->off_cn = take(4ll * B * round_up(s->mem_dim, 4));
+  ws->off_prof = take(8ll * 8 * B);
   ws->off_xw = take(4ll * B * T * 4 * C);
   ws->total = o;
 }
@@ -1228,9 +1283,11 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     if (cpl) {
       int o2 = 0;
       auto take2 = [&](int n) { int r = o2; o2 += round_up(n, 4); return r; };
-      ma.oK = take2(H * M4); ma.oE = take2(W * M4); ma.oA = take2(W * M4);
+      ma.RP = tma_rp(MC);
+      ma.oK = take2(std::max(H * M4, (ma.RP - 1) * (R + 1) * M4));   // keys, later the quad-slot partials
+      ma.oE = take2(W * M4); ma.oA = take2(W * M4);
       ma.oSim = take2(H * Npad); ma.oWg = take2(H * Npad); ma.oWn = take2(H * Npad); ma.oWp = take2(H * Npad);
-      ma.oRaw = take2(PO4);
+      ma.oRaw = take2(PO4); ma.oCn = take2(M4);
       ma.oSm = take2(4 * H + H * SMAX + (TMA_NT / 32) * H + 3 * H * std::max(1, (TMA_NT / 32) / H) + 8);
       ma.NS = TMA_NS;
       ma.RPS = tma_rps(N, M);
@@ -1238,11 +1295,11 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       while ((1 << ma.rps_shift) < ma.RPS) ++ma.rps_shift;
       ma.NCH = N / ma.RPS;
       ma.RP = tma_rp(MC);
-      ma.SPS = 4 * ma.RP / ma.RPS;
+      ma.SPS = 1;
       ma.oBar = take2(2 * (ma.NS + 1) + 2);
       o2 = round_up(o2, 32);                      // 128-byte aligned ring
       ma.oRing = o2;
-      o2 += std::max(ma.NS * ma.RPS * M, ma.RP * (R + 1) * M4);
+      o2 += ma.NS * ma.RPS * M;
       smem_tma = 4 * o2;
       ma.l2_hints = getenv("NTM_B200_NO_L2_HINTS") == nullptr ? 1 : 0;
     }
@@ -1252,6 +1309,10 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     ma.nslab = 1; ma.slab = 0; ma.bias = nullptr;
     ma.cn = cn; ma.act_read = act[0]; ma.s_act = ws.actK[0];
     ma.logits = logits; ma.outputs = outputs;
+    ma.B = B;
+    ma.vec_out = (ws.actK[0] % 4 == 0 && out->stride_read % 4 == 0 && (R * M) % 4 == 0) ? 1 : 0;
+    ma.prof = prof ? reinterpret_cast<long long*>(wsb + ws.off_prof) : nullptr;
+    g_prof_ptr = ma.prof; g_prof_B = B;
 
     for (long long t = 0; t < T; ++t) {
       const bool last = (t == T - 1);
@@ -1319,6 +1380,26 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
 }
 
 int stream_mem_occupancy() { return g_mem_occ; }
+
+// Mean duration (ns) of the memory kernel's phases over the CTAs of the last launch: {wait for the head
+// parameters, activations, pass 1, addressing, pass 2, store drain, finalize, whole CTA}; out[8] = span of
+// the launch (first CTA start to last CTA end).  Synchronous; call after the stream was synchronised.
+int stream_phase_ns(double* out9) {
+  for (int i = 0; i < 9; ++i) out9[i] = 0.0;
+  if (g_prof_ptr == nullptr || g_prof_B <= 0) return 0;
+  std::vector<long long> h((size_t)g_prof_B * 8);
+  if (cudaMemcpy(h.data(), g_prof_ptr, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  long long first = h[0], last = h[7];
+  for (long long b = 0; b < g_prof_B; ++b) {
+    const long long* r = &h[(size_t)b * 8];
+    for (int i = 0; i < 7; ++i) out9[i] += (double)(r[i + 1] - r[i]);
+    out9[7] += (double)(r[7] - r[0]);
+    first = std::min(first, r[0]); last = std::max(last, r[7]);
+  }
+  for (int i = 0; i < 8; ++i) out9[i] /= (double)g_prof_B;
+  out9[8] = (double)(last - first);
+  return (int)g_prof_B;
+}
 
 int stream_last_ms(float* out4) {
   out4[0] = out4[1] = out4[2] = out4[3] = 0.0f;

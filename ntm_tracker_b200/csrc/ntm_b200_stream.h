@@ -14,7 +14,7 @@
 namespace ntm_b200 {
 
 struct StreamWorkspace {
-  long long off_act[MAXL], off_partA, off_mc, off_cn, off_xw, total;
+  long long off_act[MAXL], off_partA, off_mc, off_cn, off_prof, off_xw, total;
   long long slabA, slabC;       // floats per K-slice slab
   int ksA[MAXL], ksC;           // K-slices of each controller GEMM / of the head-parameter GEMM
   int actK[MAXL];
@@ -38,6 +38,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
 int stream_last_ms(float* out4);
 // co-resident CTAs per SM of the memory kernel last configured (occupancy query)
 int stream_mem_occupancy();
+int stream_phase_ns(double* out9);
 
 // defined in ntm_b200.cu (the tcgen05 tile kernel lives in a header with internal linkage state)
 int gemm_tc(const float* x, int ldx, const float* w, int ldw, const float* bias, float* out, int ldo,
