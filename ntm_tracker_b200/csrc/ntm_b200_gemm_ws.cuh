@@ -1,0 +1,310 @@
+// ntm_b200_gemm_ws.cuh -- warp-specialised tcgen05 GEMM of the streaming mode:
+//
+//   out[ks][r, j] = sum_{k in slice ks} act[r, k] * W[k, j]  (+ bias[j])       r < rows, j < ncols
+//
+// the controller projection [read | h] @ W_rh and the head-parameter projection h @ [W_addr | W_out]
+// (ntm_cell.py:101-105, 113-130, 220) for ALL sequences of the shard at once.
+//
+// fp32 accuracy on the bf16 tensor pipe: both operands are split a = hi + lo (bf16 each, ~2^-18
+// relative) and D += hi*hi + hi*lo + lo*hi in fp32.  The split is done ONCE by the producers, not in
+// this kernel: activations arrive as ready-made operand tiles -- for each (128-row block, 64-wide K atom)
+// a contiguous 32 KiB record = the K-major SWIZZLE_128B shared-memory image of the hi half followed by
+// the lo half -- written by the memory kernel (read vectors) and the LSTM kernel (hidden state); weights
+// are packed the same way once per call.
+//
+// One persistent CTA per SM owns one (128-column weight tile, K-slice of KA atoms): weight hi half
+// resident in TMEM (A-from-TMEM MMAs), lo half resident in shared memory.  Roles:
+//   warp 0      producer: one 32 KiB cp.async.bulk per (row block, K atom) into a 3-slot ring
+//   warp 1      tcgen05.mma issuer (one elected lane); commits release ring slots / publish accumulators
+//   warps 2..5  epilogue: TMEM -> registers -> global, double-buffered against the next row block's MMAs
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ntm_b200_umma.cuh"
+
+namespace ntm_b200 {
+namespace gemmws {
+
+constexpr int KA_MAX = 8;            // K atoms (64 wide) per slice: 256 TMEM columns of weight hi halves
+constexpr int NSLOT = 3;             // activation ring slots (32 KiB each)
+constexpr int THREADS = 192;
+constexpr int ATOM_BYTES = 16384;    // [128 rows][128 B]
+constexpr int REC_BYTES = 2 * ATOM_BYTES;
+
+struct Args {
+  const uint8_t* act;    // [row blocks][KAtot][hi 16 KiB | lo 16 KiB]
+  const uint32_t* whi;   // [tiles][slices][128 cols][KA * 32] packed bf16 pairs (k, k+1)
+  const uint8_t* wlo;    // [tiles][slices][KA][16 KiB swizzled image]
+  const float* bias;     // [ncols] or null
+  float* out;            // slab ks at out + ks * slab, rows ldo apart
+  long long rows, slab;
+  int ldo, ncols, ntiles, kslices, ngroups, KAtot, KA;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(umma::smem_u32(dst)), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
+  using namespace umma;
+  extern __shared__ __align__(16) uint8_t ws_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x % a.ntiles;
+  const int ks = (blockIdx.x / a.ntiles) % a.kslices;
+  const int group = blockIdx.x / (a.ntiles * a.kslices);
+  const int ka0 = ks * a.KA;
+  const int nka = min(a.KA, a.KAtot - ka0);           // atoms of this slice
+  uint8_t* sWlo = smem;                                // [KA][16 KiB]
+  uint8_t* sRing = smem + (size_t)a.KA * ATOM_BYTES;   // [NSLOT][hi | lo]
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT], acc_full[2], acc_empty[2], wbar, whibar;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(&wbar, 1);
+    mbar_init(&whibar, 4);
+    fence_proxy_async_smem();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tWhi = tmem + 256;                    // accumulators: columns 0..127 and 128..255
+  const long long nrb = (a.rows + 127) / 128;
+  const size_t wrec = (size_t)tile * a.kslices + ks;   // this CTA's weight record
+
+  if (warp == 0) {
+    // ------------------------------------------------ producer ------------------------------------
+    if (lane == 0) {
+      mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
+      for (int k = 0; k < nka; ++k)
+        bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
+      uint32_t use = 0;
+      for (long long rb = group; rb < nrb; rb += a.ngroups) {
+        for (int k = 0; k < nka; ++k, ++use) {
+          const uint32_t slot = use % NSLOT;
+          mbar_wait(&empty[slot], ((use / NSLOT) & 1u) ^ 1u);      // passes on a fresh barrier
+          mbar_expect_tx(&full[slot], REC_BYTES);
+          bulk_g2s(sRing + (size_t)slot * REC_BYTES, a.act + ((size_t)rb * a.KAtot + ka0 + k) * REC_BYTES, REC_BYTES,
+                   &full[slot]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer ----------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, 128);
+      mbar_wait(&wbar, 0);       // weight lo half in shared memory (bulk copies)
+      mbar_wait(&whibar, 0);     // weight hi half in TMEM (stored by the four epilogue warps)
+      tcgen05_fence_after();
+      uint32_t use = 0, it = 0;
+      for (long long rb = group; rb < nrb; rb += a.ngroups, ++it) {
+        const uint32_t ab = it & 1u;
+        mbar_wait(&acc_empty[ab], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tAcc = tmem + ab * 128;
+        for (int k = 0; k < nka; ++k, ++use) {
+          const uint32_t slot = use % NSLOT;
+          mbar_wait(&full[slot], (use / NSLOT) & 1u);
+          tcgen05_fence_after();
+          const uint8_t* sBhi = sRing + (size_t)slot * REC_BYTES;
+          const uint8_t* sBlo = sBhi + ATOM_BYTES;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint64_t dBhi = make_sw128_desc(sBhi + s * 32);
+            const uint64_t dBlo = make_sw128_desc(sBlo + s * 32);
+            const uint64_t dWlo = make_sw128_desc(sWlo + (size_t)k * ATOM_BYTES + s * 32);
+            const uint32_t tA = tWhi + (uint32_t)(k * 64 + s * 16) / 2;
+            mma_ts(tAcc, tA, dBhi, idesc, (k == 0 && s == 0) ? 0u : 1u);
+            mma_ts(tAcc, tA, dBlo, idesc, 1u);
+            mma_ss(tAcc, dWlo, dBhi, idesc, 1u);
+          }
+          mma_commit(&empty[slot]);                                // slot reusable once these MMAs have read it
+        }
+        mma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps ------------------------------
+    const int qd = warp & 3;                            // TMEM lane quarter this warp may access
+    const uint32_t lane_addr = (uint32_t)(32 * qd) << 16;
+    const int jl = 32 * qd + lane;                      // weight column within the tile = TMEM lane
+    const int jcol = tile * 128 + jl;
+    // weight hi half -> TMEM (once)
+    {
+      const uint32_t* src = a.whi + (wrec * 128 + jl) * (size_t)(a.KA * 32);
+      for (int q = 0; q < nka * 4; ++q) {               // 16 k = 8 packed words per step
+        const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(src + q * 8));
+        const uint4 hi4 = __ldg(reinterpret_cast<const uint4*>(src + q * 8 + 4));
+        const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        tmem_st_x8(tWhi + lane_addr + q * 8, v);
+      }
+      tmem_wait_st();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&whibar);
+    }
+    const float bias = (a.bias != nullptr && jcol < a.ncols) ? __ldg(a.bias + jcol) : 0.0f;
+    float* outp = a.out + (size_t)ks * a.slab + jcol;
+    uint32_t it = 0;
+    for (long long rb = group; rb < nrb; rb += a.ngroups, ++it) {
+      const uint32_t ab = it & 1u;
+      mbar_wait(&acc_full[ab], (it >> 1) & 1u);
+      tcgen05_fence_after();
+      const long long r0 = rb * 128;
+      const uint32_t tAcc = tmem + ab * 128 + lane_addr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tAcc + c0, v);
+        tmem_wait_ld();
+        if (jcol < a.ncols) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const long long r = r0 + c0 + e;
+            if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v[e]) + bias;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// Producer-side store: 8 consecutive k (k % 8 == 0) of row r into the operand tiles.
+__device__ __forceinline__ void store_split8(uint8_t* tiles, int KAtot, long long r, int k, const float (&v)[8]) {
+  uint4 h, l;
+  umma::split_pack_bf16(v[0], v[1], h.x, l.x);
+  umma::split_pack_bf16(v[2], v[3], h.y, l.y);
+  umma::split_pack_bf16(v[4], v[5], h.z, l.z);
+  umma::split_pack_bf16(v[6], v[7], h.w, l.w);
+  const int row = (int)(r & 127);
+  uint8_t* rec = tiles + ((size_t)(r >> 7) * KAtot + (k >> 6)) * REC_BYTES +
+                 (row >> 3) * 1024 + (row & 7) * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4);
+  *reinterpret_cast<uint4*>(rec) = h;
+  *reinterpret_cast<uint4*>(rec + ATOM_BYTES) = l;
+}
+
+// ---- packing kernels ----
+// fp32 [rows, K] (row stride ld) -> operand tiles [row block][KAtot][hi | lo]; rows / k beyond the matrix
+// are written as zeros so the whole record is valid MMA input.  One thread per 8 consecutive k.
+__global__ void pack_act_tiles_kernel(const float* __restrict__ x, long long rows, int K, int ld, uint8_t* tiles,
+                                      int KAtot, int k_off) {
+  const long long nrb = (rows + 127) / 128;
+  const int KAsrc = (K + 63) / 64;
+  const long long total = nrb * 128 * (long long)KAsrc * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i & 7);
+    long long t = i >> 3;
+    const int row = (int)(t & 127); t >>= 7;
+    const int ka = (int)(t % KAsrc);
+    const long long rb = t / KAsrc;
+    const long long r = rb * 128 + row;
+    const int k = ka * 64 + chunk * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (r < rows && k + e < K) ? x[r * (long long)ld + k + e] : 0.0f;
+    uint4 h, l;
+    umma::split_pack_bf16(v[0], v[1], h.x, l.x);
+    umma::split_pack_bf16(v[2], v[3], h.y, l.y);
+    umma::split_pack_bf16(v[4], v[5], h.z, l.z);
+    umma::split_pack_bf16(v[6], v[7], h.w, l.w);
+    const int kk = k_off + k;                       // position in the destination K axis (multiple of 8)
+    if (kk >= KAtot * 64) continue;
+    uint8_t* rec = tiles + ((size_t)rb * KAtot + (kk >> 6)) * REC_BYTES +
+                   (row >> 3) * 1024 + (row & 7) * 128 + ((((kk & 63) >> 3) ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(rec) = h;
+    *reinterpret_cast<uint4*>(rec + ATOM_BYTES) = l;
+  }
+}
+
+// W [K, ncols] (row stride ldw) -> per (tile, slice): hi words [128 cols][KA*32], lo swizzled images [KA][16 KiB].
+__global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int K, int ncols, int ldw, uint32_t* whi,
+                                         uint8_t* wlo, int ntiles, int kslices, int KA) {
+  const long long total = (long long)ntiles * kslices * 128 * KA * 8;      // 8-k chunks
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int jl = (int)(i & 127);                   // column fastest: coalesced reads of W rows
+    long long t = i >> 7;
+    const int ch = (int)(t % (KA * 8)); t /= (KA * 8);
+    const int ks = (int)(t % kslices);
+    const int tile = (int)(t / kslices);
+    const int j = tile * 128 + jl;
+    const int kl = ch * 8;                           // k within the slice
+    const int k = ks * KA * 64 + kl;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (j < ncols && k + e < K) ? w[(size_t)(k + e) * ldw + j] : 0.0f;
+    uint4 h, l;
+    umma::split_pack_bf16(v[0], v[1], h.x, l.x);
+    umma::split_pack_bf16(v[2], v[3], h.y, l.y);
+    umma::split_pack_bf16(v[4], v[5], h.z, l.z);
+    umma::split_pack_bf16(v[6], v[7], h.w, l.w);
+    const size_t wrec = (size_t)tile * kslices + ks;
+    *reinterpret_cast<uint4*>(whi + (wrec * 128 + jl) * (size_t)(KA * 32) + ch * 4) = h;
+    uint8_t* img = wlo + (wrec * KA + (kl >> 6)) * ATOM_BYTES +
+                   (jl >> 3) * 1024 + (jl & 7) * 128 + ((((kl & 63) >> 3) ^ (jl & 7)) << 4);
+    *reinterpret_cast<uint4*>(img) = l;
+  }
+}
+
+struct Plan {
+  int K, ncols, KAtot, KA, kslices, ntiles, ngroups;
+  size_t whi_bytes, wlo_bytes, act_bytes;
+};
+inline Plan make_plan(int K, int ncols, long long rows, int nsm) {
+  Plan p{};
+  p.K = K; p.ncols = ncols;
+  p.KAtot = (K + 63) / 64;
+  p.KA = p.KAtot < KA_MAX ? p.KAtot : KA_MAX;
+  p.kslices = (p.KAtot + p.KA - 1) / p.KA;
+  p.KA = (p.KAtot + p.kslices - 1) / p.kslices;      // even out the slices
+  p.ntiles = (ncols + 127) / 128;
+  const long long nrb = (rows + 127) / 128;
+  const int units = p.ntiles * p.kslices;
+  long long g = nsm / (units > 0 ? units : 1);
+  if (g > nrb) g = nrb;
+  if (g < 1) g = 1;
+  p.ngroups = (int)g;
+  p.whi_bytes = (size_t)units * 128 * p.KA * 32 * 4;
+  p.wlo_bytes = (size_t)units * p.KA * ATOM_BYTES;
+  p.act_bytes = (size_t)nrb * p.KAtot * REC_BYTES;
+  return p;
+}
+inline bool plan_ok(const Plan& p, int nsm) { return p.ntiles * p.kslices <= nsm && p.KA <= KA_MAX; }
+
+inline int smem_bytes(const Plan& p) { return 1024 + p.KA * ATOM_BYTES + NSLOT * REC_BYTES; }
+
+inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi, const uint8_t* wlo, const float* bias,
+                          float* out, int ldo, long long slab, long long rows, cudaStream_t stream) {
+  Args a{};
+  a.act = act; a.whi = whi; a.wlo = wlo; a.bias = bias; a.out = out; a.rows = rows; a.slab = slab; a.ldo = ldo;
+  a.ncols = p.ncols; a.ntiles = p.ntiles; a.kslices = p.kslices; a.ngroups = p.ngroups; a.KAtot = p.KAtot; a.KA = p.KA;
+  const int smem = smem_bytes(p);
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  gemm_ws_kernel<<<p.ntiles * p.kslices * p.ngroups, THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gemmws
+}  // namespace ntm_b200

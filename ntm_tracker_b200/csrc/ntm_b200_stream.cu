@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "ntm_b200_stream.h"
+#include "ntm_b200_gemm_ws.cuh"
 
 namespace ntm_b200 {
 namespace {
@@ -65,6 +66,7 @@ struct MemArgs {
   int RPS, NS, NCH, RP, SPS, rps_shift;      // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = SPS stages
   int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
   int vec_out;                               // read-vector rows are 16-byte aligned
+  uint8_t* tilesA; int KAtotA;               // controller-GEMM operand tiles (read vectors at k = r*M + d), or null
   long long B;
   int l2_hints;
   long long* prof;                           // [B][8] phase timestamps (globaltimer ns) of the last launch, or null
@@ -918,6 +920,20 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
             if (ro) { ro[r * M] = racc[r].x; ro[r * M + 1] = racc[r].y; ro[r * M + 2] = racc[r].z; ro[r * M + 3] = racc[r].w; }
           }
         }
+      }
+      if (a.tilesA != nullptr) {
+        // next step's controller-GEMM operand: bf16 hi/lo of the read vectors, straight into the tile
+        // records (lane pairs assemble 8 consecutive columns; every thread takes part in the shuffles)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float v[8];
+          v[0] = racc[r].x; v[1] = racc[r].y; v[2] = racc[r].z; v[3] = racc[r].w;
+          v[4] = __shfl_xor_sync(0xffffffffu, racc[r].x, 1); v[5] = __shfl_xor_sync(0xffffffffu, racc[r].y, 1);
+          v[6] = __shfl_xor_sync(0xffffffffu, racc[r].z, 1); v[7] = __shfl_xor_sync(0xffffffffu, racc[r].w, 1);
+          if (worker && rp == 0 && (c & 1) == 0) gemmws::store_split8(a.tilesA, a.KAtotA, b, r * M + 4 * c, v);
+        }
+      }
+      if (worker && rp == 0) {
         float4 cn4;   // tf.nn.l2_normalize over N, ops.py:147-150
         cn4.x = 1.0f / sqrtf(fmaxf(csq.x, 1e-12f)); cn4.y = 1.0f / sqrtf(fmaxf(csq.y, 1e-12f));
         cn4.z = 1.0f / sqrtf(fmaxf(csq.z, 1e-12f)); cn4.w = 1.0f / sqrtf(fmaxf(csq.w, 1e-12f));
@@ -1019,10 +1035,13 @@ struct LstmArgs {
   float* act_self; int actK_self;        // h -> recurrent input of this layer (last C columns)
   float* act_next; int actK_next;        // h -> first C columns of the next layer's input (or null)
   float *hZ, *hC, *hH;                   // training history (or null)
+  uint8_t *tilesA, *tilesC;              // GEMM operand tiles receiving h (C % 8 == 0), or null
+  int KAtotA, koffA, KAtotC;
 };
 __global__ void lstm_stream_kernel(const LstmArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.B * a.C) return;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i0 < a.B * a.C;
+  const long long i = live ? i0 : 0;      // tail lanes recompute element 0 and store nothing
   const long long b = i / a.C;
   const int u = (int)(i - b * a.C), C = a.C;
   float z[4];
@@ -1032,18 +1051,28 @@ __global__ void lstm_stream_kernel(const LstmArgs a) {
     float v = (a.l == 0) ? __ldg(a.xw + (b * a.T + a.t) * (long long)(4 * C) + col) : __ldg(a.bias + col);
     for (int ks = 0; ks < a.KS; ++ks) v += __ldcg(a.part + (size_t)ks * a.slab + b * (long long)(4 * C) + col);
     z[q] = v;
-    if (a.hZ) a.hZ[((((size_t)a.t * a.B + b) * a.L + a.l) * 4 + q) * C + u] = v;
+    if (a.hZ && live) a.hZ[((((size_t)a.t * a.B + b) * a.L + a.l) * 4 + q) * C + u] = v;
   }
   float* cp = a.ctrl + b * a.sctrl + (2 * a.l) * C + u;
   const float c_prev = *cp;
   const float c_new = c_prev * sigmoid_f(z[2]) + sigmoid_f(z[0]) * tanh_f(z[1]);
   const float h_new = tanh_f(c_new) * sigmoid_f(z[3]);
-  cp[0] = c_new;
-  cp[C] = h_new;
-  if (a.hC) a.hC[(((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u] = c_new;
-  if (a.hH) a.hH[(((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u] = h_new;
-  a.act_self[b * a.actK_self + (a.actK_self - C) + u] = h_new;
-  if (a.act_next) a.act_next[b * a.actK_next + u] = h_new;
+  if (live) {
+    cp[0] = c_new;
+    cp[C] = h_new;
+    if (a.hC) a.hC[(((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u] = c_new;
+    if (a.hH) a.hH[(((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u] = h_new;
+    a.act_self[b * a.actK_self + (a.actK_self - C) + u] = h_new;
+    if (a.act_next) a.act_next[b * a.actK_next + u] = h_new;
+  }
+  if (a.tilesA != nullptr) {   // C % 8 == 0: aligned groups of 8 lanes hold 8 consecutive units of one sequence
+    const int lane = threadIdx.x & 31, g0 = lane & ~7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __shfl_sync(0xffffffffu, h_new, g0 + e);
+    if (live && (lane & 7) == 0) gemmws::store_split8(a.tilesA, a.KAtotA, b, a.koffA + u, v);
+    if (live && (lane & 7) == 1) gemmws::store_split8(a.tilesC, a.KAtotC, b, u - 1, v);
+  }
 }
 
 // ------------------------------------------------------------------------------------- host side --
@@ -1207,6 +1236,17 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
   ws->ksC = 1;
   ws->slabA = B * 4ll * C;
   ws->slabC = B * (long long)PO4;
+  {   // operand tiles + packed weights of the warp-specialised GEMMs (layer-0 controller, head parameters)
+    const gemmws::Plan pa = gemmws::make_plan(ws->actK[0], 4 * C, B, B200_SMS);
+    const gemmws::Plan pc = gemmws::make_plan(C, PO4, B, B200_SMS);
+    ksmax = std::max(ksmax, pa.kslices);
+    ws->off_tilesA = take((long long)pa.act_bytes);
+    ws->off_tilesC = take((long long)pc.act_bytes);
+    ws->off_whiA = take((long long)pa.whi_bytes);
+    ws->off_wloA = take((long long)pa.wlo_bytes);
+    ws->off_whiC = take((long long)pc.whi_bytes);
+    ws->off_wloC = take((long long)pc.wlo_bytes);
+  }
   ws->off_partA = take(4ll * ksmax * ws->slabA);
   ws->off_mc = take(4ll * ws->slabC);
   ws->off_cn = take(4ll * B * round_up(s->mem_dim, 4));
@@ -1263,6 +1303,37 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_small_kernel");
   }
+  // ---- warp-specialised tensor-core GEMMs (single-layer controller, M and C multiples of 8, TMA memory
+  //      kernel): operands pre-split into bf16 hi/lo tile records by their producers ----
+  const bool use_ws = (L == 1) && (M % 8 == 0) && (C % 8 == 0) && tma_rps(N, M) > 0 && tma_cpl(H, MC) > 0 &&
+                      getenv("NTM_B200_NO_TMA_RING") == nullptr && getenv("NTM_B200_OLD_GEMM") == nullptr;
+  gemmws::Plan planA{}, planC{};
+  uint8_t* tilesA = reinterpret_cast<uint8_t*>(wsb + ws.off_tilesA);
+  uint8_t* tilesC = reinterpret_cast<uint8_t*>(wsb + ws.off_tilesC);
+  uint32_t* whiA = reinterpret_cast<uint32_t*>(wsb + ws.off_whiA);
+  uint8_t* wloA = reinterpret_cast<uint8_t*>(wsb + ws.off_wloA);
+  uint32_t* whiC = reinterpret_cast<uint32_t*>(wsb + ws.off_whiC);
+  uint8_t* wloC = reinterpret_cast<uint8_t*>(wsb + ws.off_wloC);
+  bool ws_ok = false;
+  if (use_ws) {
+    planA = gemmws::make_plan(ws.actK[0], 4 * C, B, nsm);
+    planC = gemmws::make_plan(C, PO4, B, nsm);
+    ws_ok = gemmws::plan_ok(planA, nsm) && gemmws::plan_ok(planC, nsm);
+  }
+  if (ws_ok) {
+    if ((e = cudaMemsetAsync(tilesA, 0, planA.act_bytes, stream)) != cudaSuccess) return set_cuda_error_ext(e, "cudaMemsetAsync");
+    if ((e = cudaMemsetAsync(tilesC, 0, planC.act_bytes, stream)) != cudaSuccess) return set_cuda_error_ext(e, "cudaMemsetAsync");
+    const int RM = R * M;
+    gemmws::pack_act_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(act[0], B, RM, ws.actK[0], tilesA, planA.KAtot, 0);
+    gemmws::pack_act_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(act[0] + RM, B, C, ws.actK[0], tilesA, planA.KAtot, RM);
+    gemmws::pack_act_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(act[0] + RM, B, C, ws.actK[0], tilesC, planC.KAtot, 0);
+    gemmws::pack_weight_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(w->lstm_w[0] + (size_t)s->input_dim * 4 * C, ws.actK[0],
+                                                                4 * C, 4 * C, whiA, wloA, planA.ntiles, planA.kslices, planA.KA);
+    gemmws::pack_weight_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(wC, C, PO4, PO4, whiC, wloC, planC.ntiles, planC.kslices,
+                                                                planC.KA);
+    for (int i = 0; i < 5; ++i) count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "gemmws pack kernels");
+  }
   if (prof) cudaEventRecord(g_sev[1], stream);
 
   // ---- shared-memory carve-up of the memory kernel ----
@@ -1310,6 +1381,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     ma.cn = cn; ma.act_read = act[0]; ma.s_act = ws.actK[0];
     ma.logits = logits; ma.outputs = outputs;
     ma.B = B;
+    ma.tilesA = ws_ok ? tilesA : nullptr; ma.KAtotA = planA.KAtot;
     ma.vec_out = (ws.actK[0] % 4 == 0 && out->stride_read % 4 == 0 && (R * M) % 4 == 0) ? 1 : 0;
     ma.prof = prof ? reinterpret_cast<long long*>(wsb + ws.off_prof) : nullptr;
     g_prof_ptr = ma.prof; g_prof_B = B;
@@ -1320,12 +1392,21 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       // ---- controller: per layer GEMM (tensor cores) + gates ----
       for (int l = 0; l < L; ++l) {
         const float* wl = w->lstm_w[l] + (l == 0 ? (size_t)s->input_dim * 4 * C : 0);
-        int st = gemm_tc(act[l], ws.actK[l], wl, 4 * C, nullptr, partA, 4 * C, ws.slabA, B, ws.actK[l], 4 * C,
-                         ws.ksA[l], nsm, stream);
-        count_launch();
-        if (st != 0) return set_cuda_error_ext(cudaGetLastError(), "gemm_tc(controller)");
+        if (ws_ok) {
+          e = gemmws::launch(planA, tilesA, whiA, wloA, nullptr, partA, 4 * C, ws.slabA, B, stream);
+          count_launch();
+          if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(controller)");
+        } else {
+          int st = gemm_tc(act[l], ws.actK[l], wl, 4 * C, nullptr, partA, 4 * C, ws.slabA, B, ws.actK[l], 4 * C,
+                           ws.ksA[l], nsm, stream);
+          count_launch();
+          if (st != 0) return set_cuda_error_ext(cudaGetLastError(), "gemm_tc(controller)");
+        }
         LstmArgs la{};
-        la.B = B; la.C = C; la.L = L; la.l = l; la.T = (int)T; la.t = (int)t; la.KS = ws.ksA[l]; la.slab = ws.slabA;
+        la.B = B; la.C = C; la.L = L; la.l = l; la.T = (int)T; la.t = (int)t; la.KS = ws_ok ? planA.kslices : ws.ksA[l]; la.slab = ws.slabA;
+        if (ws_ok) {
+          la.tilesA = tilesA; la.tilesC = tilesC; la.KAtotA = planA.KAtot; la.koffA = R * M; la.KAtotC = planC.KAtot;
+        }
         la.xw = xw; la.bias = w->lstm_b[l]; la.part = partA;
         la.ctrl = out->controller_state; la.sctrl = out->stride_controller_state;
         la.act_self = act[l]; la.actK_self = ws.actK[l];
@@ -1339,7 +1420,11 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       if (prof) cudaEventRecord(g_sev[2 + 4 * t + 1], stream);
       // ---- head parameters + logits: one GEMM, bias folded in ----
       float* mc_t = hP ? hist->params + (size_t)t * B * PO4 : mcbuf;
-      {
+      if (ws_ok) {
+        e = gemmws::launch(planC, tilesC, whiC, wloC, bC, mc_t, PO4, 0, B, stream);
+        count_launch();
+        if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(head parameters)");
+      } else {
         int st = gemm_tc(act[L - 1] + (ws.actK[L - 1] - C), ws.actK[L - 1], wC, PO4, bC, mc_t, PO4, 0, B, C, PO4, 1,
                          nsm, stream);
         count_launch();

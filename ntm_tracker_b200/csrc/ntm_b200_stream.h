@@ -15,6 +15,7 @@ namespace ntm_b200 {
 
 struct StreamWorkspace {
   long long off_act[MAXL], off_partA, off_mc, off_cn, off_prof, off_xw, total;
+  long long off_tilesA, off_tilesC, off_whiA, off_wloA, off_whiC, off_wloC;   // warp-specialised GEMM operands
   long long slabA, slabC;       // floats per K-slice slab
   int ksA[MAXL], ksC;           // K-slices of each controller GEMM / of the head-parameter GEMM
   int actK[MAXL];
