@@ -188,6 +188,14 @@ int32_t ntm_b200_serialize_tracker_inputs(const float* features, const float* ta
 int32_t ntm_b200_gather_offsets(const float* logits, float* offsets, int64_t batch, int32_t frames,
                                 int32_t num_features, int32_t output_dim, void* stream);
 
+/* Host -> device copy of the frames [t0, t1) of every sequence: inputs_host [B, T, D] (page-locked for a
+ * truly asynchronous copy) -> frames_dev [B, t1 - t0, D] contiguous, as one strided DMA on `stream`.  Lets a
+ * caller that holds the frames on the host (the reference feeds them through feed_dict on every sess.run,
+ * direct_offset_output.py:300-330, test_tracker.py:284-299) overlap the upload of the next block of steps
+ * with ntm_b200_forward_seq on the current one (state_in of a block = state_out of the previous block). */
+int32_t ntm_b200_copy_frames_h2d(float* frames_dev, const float* inputs_host, int64_t batch, int64_t steps,
+                                 int64_t input_dim, int64_t t0, int64_t t1, void* stream);
+
 /* Backward of one BasicLSTMCell layer at one timestep for `batch` sequences (elementwise part; the
  * two GEMMs around it stay with the caller).  dh = dh_a + dh_b (dh_b may be NULL) is the gradient
  * w.r.t. the layer's new hidden state, dc [B,C] carries the cell-state gradient in and out, z holds

@@ -69,6 +69,8 @@ SYMBOLS = {
                                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ntm_b200_gather_offsets": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_void_p]),
+    "ntm_b200_copy_frames_h2d": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                             C.c_int64, C.c_void_p]),
     "ntm_b200_lstm_backward_step": (C.c_int32, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_int64, C.c_void_p]),

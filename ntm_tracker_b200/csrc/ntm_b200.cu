@@ -608,6 +608,19 @@ int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weigh
                               outputs, debug_taps, workspace, workspace_bytes, stream);
 }
 
+int32_t ntm_b200_copy_frames_h2d(float* frames_dev, const float* inputs_host, int64_t batch, int64_t steps,
+                                 int64_t input_dim, int64_t t0, int64_t t1, void* stream) {
+  if (!frames_dev || !inputs_host) return NTM_B200_ERR_NULL_POINTER;
+  if (batch < 1 || input_dim < 1 || t0 < 0 || t1 <= t0 || t1 > steps) return NTM_B200_ERR_BAD_SHAPE;
+  DeviceInfo di = device_info();
+  if (!di.ok) return NTM_B200_ERR_NO_DEVICE;
+  const size_t width = (size_t)(t1 - t0) * input_dim * sizeof(float);
+  cudaError_t e = cudaMemcpy2DAsync(frames_dev, width, inputs_host + t0 * input_dim, (size_t)steps * input_dim * sizeof(float),
+                                    width, (size_t)batch, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaMemcpy2DAsync(frames)");
+  return NTM_B200_OK;
+}
+
 int32_t ntm_b200_last_launch_info(int32_t* out16) {
   if (!out16) return NTM_B200_ERR_NULL_POINTER;
   for (int i = 0; i < 16; ++i) out16[i] = g_last_info[i];

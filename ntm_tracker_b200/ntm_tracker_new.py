@@ -27,6 +27,13 @@ class LoopNTMTracker(object):
         ``self.final_state`` (the reference's loop_vars M, w, read, controller_state)."""
         host_in = isinstance(inputs, np.ndarray) or not inputs.is_cuda
         as_numpy = isinstance(inputs, np.ndarray)
+        if host_in and inputs.ndim == 3 and self._time_blocks(inputs) > 1:
+            if inputs.shape[1] != self.sequence_length:
+                raise ValueError("inputs have %d steps but sequence_length is %d" % (inputs.shape[1], self.sequence_length))
+            if self.cell.input_dim is None:
+                self.cell.build(inputs.shape[2], self.initializer)
+            state = state or self.cell.zero_state(inputs.shape[0], self.initializer)
+            return self._call_host_time_pipelined(inputs, state, self._time_blocks(inputs))
         if host_in and inputs.ndim == 3 and self._pipeline_chunks(inputs.shape[0], inputs.shape[1]) > 1:
             x = None
             B, T, D = inputs.shape
@@ -47,6 +54,50 @@ class LoopNTMTracker(object):
             if as_numpy:
                 outputs, logits = outputs.numpy(), logits.numpy()
         return (outputs, logits)
+
+    # Host-resident frames (page-locked torch tensor): the call is cut into blocks of timesteps and the
+    # upload of block i+1 (one strided DMA, ntm_b200_copy_frames_h2d) overlaps the kernels of block i; the
+    # state is carried from block to block on the device, every sequence stays in every launch, so the
+    # kernels run at full batch.  None = automatic (4 blocks once the frames exceed 64 MB), 1 = off.
+    time_blocks = None
+
+    def _time_blocks(self, inputs):
+        if isinstance(inputs, np.ndarray) or inputs.dtype != torch.float32 or not inputs.is_contiguous() \
+                or not inputs.is_pinned():
+            return 1
+        B, T, D = inputs.shape
+        n = self.time_blocks
+        if n is None:
+            n = 4 if (B * T * D * 4 >= (64 << 20) and T >= 16) else 1
+        return max(1, min(int(n), T))
+
+    def _call_host_time_pipelined(self, xh, state, n):
+        import ctypes as C
+        from . import _cabi
+        cell, dev = self.cell, self.cell.device
+        lib = _cabi.load()
+        B, T, D = xh.shape
+        bounds = [(i * T // n, (i + 1) * T // n) for i in range(n)]
+        compute = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        copy.wait_stream(compute)
+        staged = []
+        for t0, t1 in bounds:                      # all uploads are queued on the copy stream up front
+            xd = torch.empty(B, t1 - t0, D, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copy):
+                _cabi.check(lib.ntm_b200_copy_frames_h2d(xd.data_ptr(), xh.data_ptr(), B, T, D, t0, t1,
+                                                         C.c_void_p(copy.cuda_stream)), "copy_frames_h2d")
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            staged.append((xd, ev))
+        outs, logs = [], []
+        for (t0, t1), (xd, ev) in zip(bounds, staged):
+            compute.wait_event(ev)
+            xd.record_stream(compute)
+            lg, out, state, _ = cell._run(xd, state, t1 - t0)
+            outs.append(out); logs.append(lg)
+        self.final_state = state
+        return torch.cat(outs, 1).cpu(), torch.cat(logs, 1).cpu()
 
     # Number of batch chunks a host-resident call is split into so that the host->device copy of
     # chunk i+1 overlaps the kernels of chunk i (sequences are independent, so any split is exact).

@@ -381,3 +381,30 @@ def test_streaming_mode_is_used(gemm_path):
             trk(xb)
             trk.cell.finish()
             assert _cabi.last_launch_info()["streaming"] == want
+
+
+def test_time_blocked_host_call_matches_device_call():
+    """Page-locked host frames: the call is cut into blocks of timesteps whose uploads overlap the
+    kernels of the previous block (ntm_b200_copy_frames_h2d + state carried on the device).  Same
+    results as the one-shot device-resident call (the column norms are re-derived from the carried
+    memory at each block boundary, hence a few ulp) and within the parity tolerance of the oracle."""
+    kw, _, _ = O.CONFIGS["c2_tracker"]
+    s = O.NTMShape(**kw)
+    params = O.init_params(s, 31, 0.05)
+    B, T = 12, 7
+    x = O.tracker_inputs(B, T, 77)
+    trk = make_tracker(s, params, T)
+    out_d, log_d = trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    st_d = {k: to_np(v) for k, v in trk.final_state.items()}
+    trk.time_blocks = 3
+    xh = torch.from_numpy(x).pin_memory()
+    out_h, log_h = trk(xh)
+    trk.cell.finish()
+    assert not out_h.is_cuda and tuple(log_h.shape) == (B, T, s.output_dim)
+    assert maxerr(to_np(log_h), to_np(log_d)) <= 1e-5
+    assert maxerr(to_np(out_h), to_np(out_d)) <= 1e-5
+    for k in ("M", "w", "read", "controller_state"):
+        assert maxerr(to_np(trk.final_state[k]), st_d[k]) <= 1e-5, k
+    ro, rl, rs = O.run_sequence(params, s, x)
+    assert maxerr(to_np(log_h), rl) <= TOL and maxerr(to_np(trk.final_state["M"]), rs["M"]) <= TOL
