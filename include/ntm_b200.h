@@ -233,8 +233,9 @@ int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms);
 int32_t ntm_b200_last_stream_ms(float* out4, int32_t* steps);
 /* Streaming mode, profiling enabled: mean duration in ns, over the CTAs (= sequences) of the last
  * memory-kernel launch, of {wait for the head parameters, activations, pass 1, addressing, pass 2, store
- * drain, finalize, whole CTA}; out9[8] = first CTA start to last CTA end.  Synchronous. */
-int32_t ntm_b200_stream_phase_ns(double* out9, int32_t* ctas);
+ * drain, finalize, whole CTA}; out12[8] = first CTA start to last CTA end; out12[9..11] = SM cycles warp 0
+ * spent in pass 1 {waiting for ring stages, computing, team barrier + bulk-copy issue}.  Synchronous. */
+int32_t ntm_b200_stream_phase_ns(double* out12, int32_t* ctas);
 /* With profiling enabled the persistent kernel also accumulates, per CTA, SM-clock
  * cycles spent in each phase of the timestep (16 int64 slots per CTA: 0/2/4/6 =
  * phases A/B/C/D compute, 1/3/5/7 = the device-wide barrier after each, 8 =

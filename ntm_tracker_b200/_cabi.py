@@ -141,10 +141,11 @@ def last_stream_ms():
 
 def stream_phase_ns():
     """Streaming mode, profiling enabled: mean ns per phase of the memory kernel's CTAs in the last launch."""
-    buf = (C.c_double * 9)()
+    buf = (C.c_double * 12)()
     n = C.c_int32(0)
     check(load().ntm_b200_stream_phase_ns(buf, C.byref(n)), "stream_phase_ns")
-    keys = ("wait_params", "activations", "pass1", "addressing", "pass2", "store_drain", "finalize", "cta", "launch_span")
+    keys = ("wait_params", "activations", "pass1", "addressing", "pass2", "store_drain", "finalize", "cta", "launch_span",
+            "p1_wait_cycles", "p1_compute_cycles", "p1_sync_issue_cycles")
     d = dict(zip(keys, list(buf)))
     d["ctas"] = n.value
     return d

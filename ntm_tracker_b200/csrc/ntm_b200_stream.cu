@@ -44,6 +44,8 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 inline long long align_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
+// (Measured negative result: rewriting the two passes with the packed fp32x2 FMA of sm_100, __ffma2_rn, made
+// the kernel slower -- 460 -> 543 us per step of 4096 sequences -- so the FMAs below stay scalar.)
 constexpr int RB = 4;        // rows per transposing reduction group in pass 1
 constexpr int RB1 = 8;       // rows a warp streams at once in pass 1 (two groups)
 constexpr int U2 = 8;        // rows a thread keeps in flight in pass 2
@@ -497,7 +499,7 @@ __device__ __forceinline__ long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define MEM_PROF(slot) do { if (a.prof != nullptr && tid == 0) a.prof[(size_t)b * 8 + (slot)] = gtimer(); } while (0)
+#define MEM_PROF(slot) do { if (a.prof != nullptr && tid == 0) a.prof[(size_t)b * 16 + (slot)] = gtimer(); } while (0)
 template <int NKEEP>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NKEEP) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
@@ -551,13 +553,20 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   const int G = gridDim.x;
   const int nseq = ((int)a.B - (int)blockIdx.x + G - 1) / G;
   const int QPS = 2 * NCH, QT = nseq * QPS;
-  auto issue_load = [&](int Qg) {
-    const int si = Qg / QPS, Q = Qg - si * QPS;
+  // (si, Q): sequence slot of this CTA and stage use within it; Qg = si * QPS + Q
+  auto issue_load = [&](int si, int Q) {
+    const int Qg = si * QPS + Q;
     const int j = Q < NCH ? Q : Q - NCH;
     const float* src = a.Min + (size_t)(blockIdx.x + si * G) * a.sMin + (size_t)j * stage_floats;
     uint64_t* fb = bars + (Qg & (NS - 1));
     mbar_expect_tx(fb, stage_bytes);
     bulk_load(ring + (Qg & (NS - 1)) * stage_floats, src, stage_bytes, fb, Q < NCH ? pol_keep : pol_drop, hint);
+  };
+  // the use NS after (si, Q): same sequence or the head of the next one (nothing past the CTA's last)
+  auto issue_next = [&](int si, int Q) {
+    int s2 = si, Q2 = Q + NS;
+    while (Q2 >= QPS) { Q2 -= QPS; ++s2; }
+    if (s2 < nseq) issue_load(s2, Q2);
   };
   // head parameters, entering weightings and inverse column norms of sequence si -> shared memory
   const uint32_t par_bytes = (uint32_t)(a.PO4 + H * N + M4) * 4u;
@@ -577,7 +586,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   __syncthreads();            // barrier inits visible to every thread before anyone polls
   if (tid == 0 && nseq > 0) {
     issue_params(0);
-    for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg);
+    for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg / QPS, Qg % QPS);
   }
 
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
@@ -666,9 +675,15 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
       // consumed last -- an mbarrier cannot be waited on two phases ahead): team = slot, member = quad parity
       constexpr int WPS = NWARP / NS;
       const int team = warp % NS, member = warp / NS;
+#ifdef NTM_PROF_PASS1
+      long long pw = 0, pc = 0, pi = 0, tt = clock64();
+#endif
       for (int q = team; q < NCH; q += NS) {
         const int Qg = Qb + q;
         mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
+#ifdef NTM_PROF_PASS1
+        if (a.prof != nullptr && tid == 0) { const long long n = clock64(); pw += n - tt; tt = n; }
+#endif
         const float* sp = ring + (Qg & (NS - 1)) * stage_floats + 4 * lane + member * RB * M;
         float* simq = simS + vh * Npad + q * RPS + vi;
         for (int g0 = member * RB; g0 < RPS; g0 += WPS * RB, sp += WPS * RB * M) {
@@ -715,9 +730,20 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           if (lane < RB * H) simq[g0] = v[0];
         }
         // the team were the stage's only readers: once all of them are done, refill the slot with use Qg + NS
+#ifdef NTM_PROF_PASS1
+        if (a.prof != nullptr && tid == 0) { const long long n = clock64(); pc += n - tt; tt = n; }
+#endif
         asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPS) : "memory");
-        if (member == 0 && lane == 0 && Qg + NS < QT) issue_load(Qg + NS);
+        if (member == 0 && lane == 0) issue_next(si, q);
+#ifdef NTM_PROF_PASS1
+        if (a.prof != nullptr && tid == 0) { const long long n = clock64(); pi += n - tt; tt = n; }
+#endif
       }
+#ifdef NTM_PROF_PASS1   // build with NTM_B200_NVCC_EXTRA=-DNTM_PROF_PASS1: SM cycles warp 0 waits / computes / syncs+issues
+      if (a.prof != nullptr && tid == 0) {
+        a.prof[(size_t)b * 16 + 8] = pw; a.prof[(size_t)b * 16 + 9] = pc; a.prof[(size_t)b * 16 + 10] = pi;
+      }
+#endif
     }
     __syncthreads();
     MEM_PROF(3);
@@ -862,25 +888,22 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
               mn.x = fmaf(m[i].x, E.x, A.x); mn.y = fmaf(m[i].y, E.y, A.y);
               mn.z = fmaf(m[i].z, E.z, A.z); mn.w = fmaf(m[i].w, E.w, A.w);
             }
-            const float4 mu = a.write_first ? mn : m[i];
+            if (a.write_first) m[i] = mn;     // read from the updated memory (ntm_cell.py:212-215); uniform branch
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               const float wr = wsel(r);
-              racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
-              racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
+              racc[r].x = fmaf(wr, m[i].x, racc[r].x); racc[r].y = fmaf(wr, m[i].y, racc[r].y);
+              racc[r].z = fmaf(wr, m[i].z, racc[r].z); racc[r].w = fmaf(wr, m[i].w, racc[r].w);
             }
             csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
             csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
-            st_global_hint(gp + (size_t)i * M, mn, pol_drop, hint);
+            __stcg(reinterpret_cast<float4*>(gp + (size_t)i * M), mn);
           }
         }
         __syncthreads();         // every reader of this iteration's stage is done
         // one bulk copy costs its issuing thread ~240 ns (tools/tma_probe.cu): rotate the issuer over the
         // warps so that no warp pays it twice in a row
-        if (tid == ((it & (NWARP - 1)) << 5)) {
-          const int Qn = Qb + NCH + it + NS;
-          if (Qn < QT) issue_load(Qn);
-        }
+        if (tid == ((it & (NWARP - 1)) << 5)) issue_next(si, NCH + it);
       }
     }
     MEM_PROF(5);
@@ -1250,7 +1273,7 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
   ws->off_partA = take(4ll * ksmax * ws->slabA);
   ws->off_mc = take(4ll * ws->slabC);
   ws->off_cn = take(4ll * B * round_up(s->mem_dim, 4));
-  ws->off_prof = take(8ll * 8 * B);
+  ws->off_prof = take(8ll * 16 * B);
   ws->off_xw = take(4ll * B * T * 4 * C);
   ws->total = o;
 }
@@ -1470,19 +1493,21 @@ int stream_mem_occupancy() { return g_mem_occ; }
 // parameters, activations, pass 1, addressing, pass 2, store drain, finalize, whole CTA}; out[8] = span of
 // the launch (first CTA start to last CTA end).  Synchronous; call after the stream was synchronised.
 int stream_phase_ns(double* out9) {
-  for (int i = 0; i < 9; ++i) out9[i] = 0.0;
+  for (int i = 0; i < 12; ++i) out9[i] = 0.0;
   if (g_prof_ptr == nullptr || g_prof_B <= 0) return 0;
-  std::vector<long long> h((size_t)g_prof_B * 8);
+  std::vector<long long> h((size_t)g_prof_B * 16);
   if (cudaMemcpy(h.data(), g_prof_ptr, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
   long long first = h[0], last = h[7];
   for (long long b = 0; b < g_prof_B; ++b) {
-    const long long* r = &h[(size_t)b * 8];
+    const long long* r = &h[(size_t)b * 16];
     for (int i = 0; i < 7; ++i) out9[i] += (double)(r[i + 1] - r[i]);
     out9[7] += (double)(r[7] - r[0]);
     first = std::min(first, r[0]); last = std::max(last, r[7]);
   }
   for (int i = 0; i < 8; ++i) out9[i] /= (double)g_prof_B;
   out9[8] = (double)(last - first);
+  for (long long b = 0; b < g_prof_B; ++b)
+    for (int i = 0; i < 3; ++i) out9[9 + i] += (double)h[(size_t)b * 16 + 8 + i] / (double)g_prof_B;
   return (int)g_prof_B;
 }
 

@@ -15,11 +15,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 // mode 0: TMA ring, one thread waits + re-issues.  mode 1: plain LDG.128 by 256 threads, `ns` loads in flight each.
-__global__ void __launch_bounds__(256) probe(const float4* src, size_t bytes_per_cta, int stage_bytes, int ns, int mode, float* sink) {
+__global__ void __launch_bounds__(256) probe(const float4* src, size_t bytes_per_cta, int stage_bytes, int ns, int mode, float* sink, int reps = 1) {
   extern __shared__ float4 smem[];
   __shared__ uint64_t bars[32];
   const char* base = reinterpret_cast<const char*>(src) + (size_t)blockIdx.x * bytes_per_cta;
-  const int nstage = (int)(bytes_per_cta / stage_bytes);
+  const int nwin = (int)(bytes_per_cta / stage_bytes);
+  const int nstage = nwin * reps;
   if (mode == 0) {
     if (threadIdx.x == 0) {
       for (int i = 0; i < ns; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(s_u32(&bars[i])));
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(256) probe(const float4* src, size_t bytes_per
         if (q < nstage) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(&bars[q % ns])), "r"(stage_bytes) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                       ::"r"(s_u32(reinterpret_cast<char*>(smem) + (size_t)(q % ns) * stage_bytes)), "l"(base + (size_t)q * stage_bytes),
+                       ::"r"(s_u32(reinterpret_cast<char*>(smem) + (size_t)(q % ns) * stage_bytes)), "l"(base + (size_t)(q % nwin) * stage_bytes),
                          "r"(stage_bytes), "r"(s_u32(&bars[q % ns])) : "memory");
         }
       }
@@ -79,5 +80,22 @@ int main() {
           printf("%s %d %5.0f %2d %6.0f  %8.0f  %6.1f %s\n", mode ? "ldg" : "tma", per_sm, sb / 1024.0, ns,
                  mode ? ns * 4.0 : sb * ns / 1024.0, gbs, gbs / 148, err ? cudaGetErrorString(err) : "");
         }
+  // L2-resident source: every CTA streams the same 32 MiB window over and over (TMA ring, 16 KiB stages)
+  printf("L2-resident source (32 MiB window):\nctas/sm stageKB ns  GB/s(chip)  GB/s(per CTA)  implied latency us\n");
+  for (int per_sm = 1; per_sm <= 2; ++per_sm)
+    for (int sb : {8192, 16384})
+      for (int ns : {1, 2, 4}) {
+        const int grid = 148 * per_sm;
+        const size_t per_cta = (32u << 20) / grid / sb * sb;
+        for (int rep = 0; rep < 3; ++rep) {
+          cudaEventRecord(e0);
+          probe<<<grid, 256, sb * ns>>>(buf, per_cta, sb, ns, 0, sink, 64);
+          cudaEventRecord(e1);
+          cudaEventSynchronize(e1);
+        }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double gbs = 64.0 * per_cta * grid / (ms * 1e-3) / 1e9;
+        printf("%d %5.0f %2d  %8.0f  %6.1f  %5.2f\n", per_sm, sb / 1024.0, ns, gbs, gbs / grid, sb * ns / (gbs / grid * 1e3));
+      }
   return 0;
 }
