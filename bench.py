@@ -282,7 +282,7 @@ def main():
     x_host = make_inputs_torch(kind, B_local, T, D, 1000 + rank).pin_memory()
     x_dev = x_host.to(dev)
     lib = _cabi.load()
-    lib.ntm_b200_set_profiling(1)
+    lib.ntm_b200_set_profiling(0 if os.environ.get("NTM_BENCH_NO_PROFILING") else 1)
     plan = trk.cell.plan(B_local, T)
 
     input_bytes = x_dev.numel() * 4

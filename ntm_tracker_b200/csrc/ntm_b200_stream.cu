@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "ntm_b200_stream.h"
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
 // stage in place and hands it to a bulk store.  Bytes in flight per CTA = the ring, independent of
 // registers and occupancy -- which is what an HBM-latency-bound stream needs.
 constexpr int TMA_NT = 256;
-constexpr int TMA_NS = 4;     // ring stages (one stage = the rows of one pass-2 iteration, 16 KiB at M*RP = 1024)
+constexpr int TMA_NS = 8;     // ring stages (one stage = half the rows of a pass-2 iteration, 8 KiB at M*RP = 1024)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
@@ -553,20 +554,15 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   const int G = gridDim.x;
   const int nseq = ((int)a.B - (int)blockIdx.x + G - 1) / G;
   const int QPS = 2 * NCH, QT = nseq * QPS;
-  // (si, Q): sequence slot of this CTA and stage use within it; Qg = si * QPS + Q
-  auto issue_load = [&](int si, int Q) {
-    const int Qg = si * QPS + Q;
+  // (the division runs on the issuing lane only, ~32 times per sequence; carrying (sequence, use) pairs
+  // instead costs registers this kernel does not have: it spilled and ran 11 % slower)
+  auto issue_load = [&](int Qg) {
+    const int si = Qg / QPS, Q = Qg - si * QPS;
     const int j = Q < NCH ? Q : Q - NCH;
     const float* src = a.Min + (size_t)(blockIdx.x + si * G) * a.sMin + (size_t)j * stage_floats;
     uint64_t* fb = bars + (Qg & (NS - 1));
     mbar_expect_tx(fb, stage_bytes);
     bulk_load(ring + (Qg & (NS - 1)) * stage_floats, src, stage_bytes, fb, Q < NCH ? pol_keep : pol_drop, hint);
-  };
-  // the use NS after (si, Q): same sequence or the head of the next one (nothing past the CTA's last)
-  auto issue_next = [&](int si, int Q) {
-    int s2 = si, Q2 = Q + NS;
-    while (Q2 >= QPS) { Q2 -= QPS; ++s2; }
-    if (s2 < nseq) issue_load(s2, Q2);
   };
   // head parameters, entering weightings and inverse column norms of sequence si -> shared memory
   const uint32_t par_bytes = (uint32_t)(a.PO4 + H * N + M4) * 4u;
@@ -586,7 +582,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   __syncthreads();            // barrier inits visible to every thread before anyone polls
   if (tid == 0 && nseq > 0) {
     issue_params(0);
-    for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg / QPS, Qg % QPS);
+    for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg);
   }
 
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
@@ -594,7 +590,6 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   const int RP = a.RP;                         // pass 2: RP quads of 4 rows per iteration = one stage
   const bool worker = tid < RP * MC;
   const int rp = worker ? tid / MC : 0, c = worker ? tid - rp * MC : 0;
-  const int vi = lane / H, vh = lane - vi * H;   // value index of the transposing reduction -> (row, head)
 
   for (int si = 0; si < nseq; ++si) {
     const int b = blockIdx.x + si * G;
@@ -671,35 +666,34 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           const int cc = lane + 32 * j;
           kr[h][j] = cc < MC ? *reinterpret_cast<const float4*>(kS + h * M4 + 4 * cc) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      // NWARP / NS warps share a stage (a warp may only wait on the use that directly follows the one it
-      // consumed last -- an mbarrier cannot be waited on two phases ahead): team = slot, member = quad parity
-      constexpr int WPS = NWARP / NS;
-      const int team = warp % NS, member = warp / NS;
-#ifdef NTM_PROF_PASS1
-      long long pw = 0, pc = 0, pi = 0, tt = clock64();
-#endif
-      for (int q = team; q < NCH; q += NS) {
+      // NTEAM teams of two warps; team t consumes the stages q = t, t + NTEAM, ... which alternate between
+      // the slots t and t + NTEAM of the ring, so the team's next stage is already in flight while it works
+      // on the current one (a warp only ever waits on the use that directly follows the one it consumed in
+      // that slot -- an mbarrier cannot be waited on two phases ahead).  Within a quad of four rows the two
+      // members take two rows each.
+      constexpr int NTEAM = NS / 2, WPT = NWARP / NTEAM;
+      static_assert(WPT == 2, "two warps per team");
+      const int team = warp % NTEAM, member = warp / NTEAM;
+      const int rv = (lane & 15) / H, hv = (lane & 15) - rv * H;      // reduced value index -> (row of the pair, head)
+      for (int q = team; q < NCH; q += NTEAM) {
         const int Qg = Qb + q;
         mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
-#ifdef NTM_PROF_PASS1
-        if (a.prof != nullptr && tid == 0) { const long long n = clock64(); pw += n - tt; tt = n; }
-#endif
-        const float* sp = ring + (Qg & (NS - 1)) * stage_floats + 4 * lane + member * RB * M;
-        float* simq = simS + vh * Npad + q * RPS + vi;
-        for (int g0 = member * RB; g0 < RPS; g0 += WPS * RB, sp += WPS * RB * M) {
-          float acc[RB][H];
+        const float* sp = ring + (Qg & (NS - 1)) * stage_floats + 4 * lane + 2 * member * M;
+        float* simq = simS + hv * Npad + q * RPS + 2 * member + rv;
+        for (int g0 = 0; g0 < RPS; g0 += RB, sp += RB * M) {
+          float acc[2][H];
 #pragma unroll
-          for (int i = 0; i < RB; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int h = 0; h < H; ++h) acc[i][h] = 0.0f;
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
             if (lane + 32 * j < MC) {
-              float4 m4[RB];
+              float4 m4[2];
 #pragma unroll
-              for (int i = 0; i < RB; ++i) m4[i] = *reinterpret_cast<const float4*>(sp + i * M + 128 * j);
+              for (int i = 0; i < 2; ++i) m4[i] = *reinterpret_cast<const float4*>(sp + i * M + 128 * j);
 #pragma unroll
-              for (int i = 0; i < RB; ++i)
+              for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                   acc[i][h] = fmaf(m4[i].x, kr[h][j].x, acc[i][h]);
@@ -709,16 +703,20 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
                 }
             }
           }
-          // transposing reduction of the RB*H <= 32 values: lane L ends with the warp total of value L
-          float v[32];
+          // reduction of the 2*H <= 16 values over the warp: one butterfly step over the half-warps, then
+          // a transposing reduction over 16 lanes (at offset o a lane keeps one half of its value list and
+          // receives the partner's sums of that half): lane L ends with the total of value L & 15
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+          for (int j = 0; j < 16; ++j) v[j] = 0.0f;
 #pragma unroll
-          for (int i = 0; i < RB; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int h = 0; h < H; ++h) v[i * H + h] = acc[i][h];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
+          for (int j = 0; j < 2 * H; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
             const bool up = (lane & o) != 0;
 #pragma unroll
             for (int j = 0; j < o; ++j) {
@@ -727,23 +725,12 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
               v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
-          if (lane < RB * H) simq[g0] = v[0];
+          if (lane < 2 * H) simq[g0] = v[0];
         }
-        // the team were the stage's only readers: once all of them are done, refill the slot with use Qg + NS
-#ifdef NTM_PROF_PASS1
-        if (a.prof != nullptr && tid == 0) { const long long n = clock64(); pc += n - tt; tt = n; }
-#endif
-        asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPS) : "memory");
-        if (member == 0 && lane == 0) issue_next(si, q);
-#ifdef NTM_PROF_PASS1
-        if (a.prof != nullptr && tid == 0) { const long long n = clock64(); pi += n - tt; tt = n; }
-#endif
+        // the team were the stage's only readers: once both members are done, refill the slot with use Qg + NS
+        asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPT) : "memory");
+        if (member == 0 && lane == 0 && Qg + NS < QT) issue_load(Qg + NS);
       }
-#ifdef NTM_PROF_PASS1   // build with NTM_B200_NVCC_EXTRA=-DNTM_PROF_PASS1: SM cycles warp 0 waits / computes / syncs+issues
-      if (a.prof != nullptr && tid == 0) {
-        a.prof[(size_t)b * 16 + 8] = pw; a.prof[(size_t)b * 16 + 9] = pc; a.prof[(size_t)b * 16 + 10] = pi;
-      }
-#endif
     }
     __syncthreads();
     MEM_PROF(3);
@@ -849,14 +836,16 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         e4[h] = *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c);
         a4[h] = *reinterpret_cast<const float4*>(aS + h * M4 + 4 * c);
       }
-      const int RS = 4 * RP;                       // rows per iteration = rows per stage
+      const int RS = 4 * RP;                       // rows per iteration = two stages
+      const int qps = RP >> 1;                     // quads per stage
+      const int sk = rp >= qps ? 1 : 0;            // which of the iteration's two stages this thread's quad is in
       int it = 0;
       for (int nb = 0; nb < N; nb += RS, ++it) {
         const int n0 = nb + 4 * rp;                // this thread's quad
         if (worker && n0 < N) {
-          const int Qg = Qb + NCH + it;
+          const int Qg = Qb + NCH + 2 * it + sk;
           mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
-          const float* mp = ring + (Qg & (NS - 1)) * stage_floats + 4 * rp * M + 4 * c;
+          const float* mp = ring + (Qg & (NS - 1)) * stage_floats + 4 * (rp - sk * qps) * M + 4 * c;
           float* gp = Mo + (size_t)n0 * M + 4 * c;
           float4 wv[H];                            // the four rows' weights of every head
 #pragma unroll
@@ -864,46 +853,55 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           float4 m[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) m[i] = *reinterpret_cast<const float4*>(mp + i * M);
+          // (write_first is uniform: the branch is taken once per quad, outside the unrolled row loop, so
+          // the four rows' FMA chains still interleave)
+          auto quad = [&](auto wf_tag) {
+            constexpr bool WF = decltype(wf_tag)::value;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            auto wsel = [&](int h) -> float { return i == 0 ? wv[h].x : (i == 1 ? wv[h].y : (i == 2 ? wv[h].z : wv[h].w)); };
-            float4 mn;
-            if constexpr (W == 1) {
-              // one write head: M' = M (1 - w e) + w a = M + w (a - M e)
-              const float ww = wsel(R);
-              mn.x = fmaf(ww, fmaf(-m[i].x, e4[0].x, a4[0].x), m[i].x);
-              mn.y = fmaf(ww, fmaf(-m[i].y, e4[0].y, a4[0].y), m[i].y);
-              mn.z = fmaf(ww, fmaf(-m[i].z, e4[0].z, a4[0].z), m[i].z);
-              mn.w = fmaf(ww, fmaf(-m[i].w, e4[0].w, a4[0].w), m[i].w);
-            } else {
-              float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i) {
+              auto wsel = [&](int h) -> float { return i == 0 ? wv[h].x : (i == 1 ? wv[h].y : (i == 2 ? wv[h].z : wv[h].w)); };
+              float4 mn;
+              if constexpr (W == 1) {
+                // one write head: M' = M (1 - w e) + w a = M + w (a - M e)
+                const float ww = wsel(R);
+                mn.x = fmaf(ww, fmaf(-m[i].x, e4[0].x, a4[0].x), m[i].x);
+                mn.y = fmaf(ww, fmaf(-m[i].y, e4[0].y, a4[0].y), m[i].y);
+                mn.z = fmaf(ww, fmaf(-m[i].z, e4[0].z, a4[0].z), m[i].z);
+                mn.w = fmaf(ww, fmaf(-m[i].w, e4[0].w, a4[0].w), m[i].w);
+              } else {
+                float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int h = 0; h < W; ++h) {
-                const float ww = wsel(R + h);
-                E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
-                E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
-                A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
-                A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
+                for (int h = 0; h < W; ++h) {
+                  const float ww = wsel(R + h);
+                  E.x *= (1.0f - ww * e4[h].x); E.y *= (1.0f - ww * e4[h].y);
+                  E.z *= (1.0f - ww * e4[h].z); E.w *= (1.0f - ww * e4[h].w);
+                  A.x = fmaf(ww, a4[h].x, A.x); A.y = fmaf(ww, a4[h].y, A.y);
+                  A.z = fmaf(ww, a4[h].z, A.z); A.w = fmaf(ww, a4[h].w, A.w);
+                }
+                mn.x = fmaf(m[i].x, E.x, A.x); mn.y = fmaf(m[i].y, E.y, A.y);
+                mn.z = fmaf(m[i].z, E.z, A.z); mn.w = fmaf(m[i].w, E.w, A.w);
               }
-              mn.x = fmaf(m[i].x, E.x, A.x); mn.y = fmaf(m[i].y, E.y, A.y);
-              mn.z = fmaf(m[i].z, E.z, A.z); mn.w = fmaf(m[i].w, E.w, A.w);
-            }
-            if (a.write_first) m[i] = mn;     // read from the updated memory (ntm_cell.py:212-215); uniform branch
+              const float4 mu = WF ? mn : m[i];   // read from the updated memory when write_first (ntm_cell.py:212-215)
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const float wr = wsel(r);
-              racc[r].x = fmaf(wr, m[i].x, racc[r].x); racc[r].y = fmaf(wr, m[i].y, racc[r].y);
-              racc[r].z = fmaf(wr, m[i].z, racc[r].z); racc[r].w = fmaf(wr, m[i].w, racc[r].w);
+              for (int r = 0; r < R; ++r) {
+                const float wr = wsel(r);
+                racc[r].x = fmaf(wr, mu.x, racc[r].x); racc[r].y = fmaf(wr, mu.y, racc[r].y);
+                racc[r].z = fmaf(wr, mu.z, racc[r].z); racc[r].w = fmaf(wr, mu.w, racc[r].w);
+              }
+              csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
+              csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
+              st_global_hint(gp + (size_t)i * M, mn, pol_drop, hint);   // evict-first: M' is not needed for a whole step
             }
-            csq.x = fmaf(mn.x, mn.x, csq.x); csq.y = fmaf(mn.y, mn.y, csq.y);
-            csq.z = fmaf(mn.z, mn.z, csq.z); csq.w = fmaf(mn.w, mn.w, csq.w);
-            __stcg(reinterpret_cast<float4*>(gp + (size_t)i * M), mn);
-          }
+          };
+          if (a.write_first) quad(std::true_type{}); else quad(std::false_type{});
         }
         __syncthreads();         // every reader of this iteration's stage is done
         // one bulk copy costs its issuing thread ~240 ns (tools/tma_probe.cu): rotate the issuer over the
         // warps so that no warp pays it twice in a row
-        if (tid == ((it & (NWARP - 1)) << 5)) issue_next(si, NCH + it);
+        if ((tid & 31) == 0 && ((warp - 2 * it) & (NWARP - 1)) < 2) {   // two issuers, rotating over the warps
+          const int Qn = Qb + NCH + 2 * it + ((warp - 2 * it) & (NWARP - 1)) + NS;
+          if (Qn < QT) issue_load(Qn);
+        }
       }
     }
     MEM_PROF(5);
@@ -1195,8 +1193,8 @@ cudaError_t launch_tma(int R, int W, int CPL, const MemArgs& a, long long B, int
   }
   return cudaErrorInvalidValue;
 }
-// Rows per ring stage = the rows one pass-2 iteration covers (4 * RP; 16 KiB when MC divides 256);
-// must divide N.  0 = shape not covered (the generic kernel runs).
+// Rows per ring stage = half the rows one pass-2 iteration covers (2 * RP; 8 KiB when MC divides 256);
+// the iteration's rows must divide N.  0 = shape not covered (the generic kernel runs).
 int tma_rp(int MC) {   // quads per pass-2 iteration: the largest power of two <= NT / MC
   int rp = 1;
   while (2 * rp * MC <= TMA_NT) rp *= 2;
@@ -1204,8 +1202,10 @@ int tma_rp(int MC) {   // quads per pass-2 iteration: the largest power of two <
 }
 int tma_rps(int N, int M) {
   if (M % 4 != 0 || M > 512) return 0;
-  const int rs = 4 * tma_rp(M / 4);            // rows of one pass-2 iteration
-  return (N % rs == 0) ? rs : 0;
+  const int rp = tma_rp(M / 4);
+  if (rp < 2) return 0;
+  const int rs = 4 * rp;                       // rows of one pass-2 iteration = two stages
+  return (N % rs == 0) ? rs / 2 : 0;
 }
 // 0 when the TMA-ring kernel does not cover the shape (then the generic register-streaming kernel runs)
 int tma_cpl(int H, int MC) {
@@ -1407,6 +1407,8 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     ma.tilesA = ws_ok ? tilesA : nullptr; ma.KAtotA = planA.KAtot;
     ma.vec_out = (ws.actK[0] % 4 == 0 && out->stride_read % 4 == 0 && (R * M) % 4 == 0) ? 1 : 0;
     ma.prof = prof ? reinterpret_cast<long long*>(wsb + ws.off_prof) : nullptr;
+    if (prof && (e = cudaMemsetAsync(wsb + ws.off_prof, 0, 8ll * 16 * B, stream)) != cudaSuccess)
+      return set_cuda_error_ext(e, "cudaMemsetAsync(prof)");
     g_prof_ptr = ma.prof; g_prof_B = B;
 
     for (long long t = 0; t < T; ++t) {
