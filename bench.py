@@ -282,7 +282,7 @@ def main():
     x_host = make_inputs_torch(kind, B_local, T, D, 1000 + rank).pin_memory()
     x_dev = x_host.to(dev)
     lib = _cabi.load()
-    lib.ntm_b200_set_profiling(0 if os.environ.get("NTM_BENCH_NO_PROFILING") else 1)
+    lib.ntm_b200_set_profiling(0)
     plan = trk.cell.plan(B_local, T)
 
     input_bytes = x_dev.numel() * 4
@@ -311,31 +311,46 @@ def main():
     trk.cell.finish()
 
     # ---------------- device-resident timing: K steps, CUDA events, max over ranks ---------
+    # Two back-to-back timed regions of K steps each.  Region 1 is the one `value` comes from: nothing but
+    # the hot path between the step events.  Region 2 repeats the same K steps with the library's per-kernel
+    # CUDA events switched on (recorded on the launching stream, between the kernels of every step); the
+    # roofline's kernel duration comes from there.  They are separate because those ~4 extra event records
+    # per timestep cost the streaming mode up to 10 % at small per-GPU batches (512 sequences), and the
+    # headline must not pay for its own instrumentation; both step times are reported.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    seq_ms, xp_ms, stream_ms = [], [], []
-    launches0 = lib.ntm_b200_launch_count()
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.fill_(i & 0xff)
-        ev[i][0].record()
-        one_step()
-        ev[i][1].record()
-        ev[i][1].synchronize()
-        a, b = C.c_float(), C.c_float()
-        lib.ntm_b200_last_kernel_ms(C.byref(a), C.byref(b))
-        xp_ms.append(a.value); seq_ms.append(b.value)
-        stream_ms.append(_cabi.last_stream_ms())
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    launches = lib.ntm_b200_launch_count() - launches0
+
+    def timed_region(profiled):
+        lib.ntm_b200_set_profiling(1 if profiled else 0)
+        one_step()                              # settle (event creation, workspace) outside the region
+        trk.cell.finish()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps)]
+        k_seq, k_xp, k_stream = [], [], []
+        barrier()
+        l0 = lib.ntm_b200_launch_count()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            if flush is not None:
+                flush.fill_(i & 0xff)
+            evs[i][0].record()
+            one_step()
+            evs[i][1].record()
+            evs[i][1].synchronize()
+            if profiled:
+                a, b = C.c_float(), C.c_float()
+                lib.ntm_b200_last_kernel_ms(C.byref(a), C.byref(b))
+                k_xp.append(a.value); k_seq.append(b.value)
+                k_stream.append(_cabi.last_stream_ms())
+        barrier()
+        wall_s = time.perf_counter() - t0
+        ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+        return ms, wall_s, k_seq, k_xp, k_stream, lib.ntm_b200_launch_count() - l0
+
+    step_ms, wall, _, _, _, launches = timed_region(False)
+    prof_step_ms, _, seq_ms, xp_ms, stream_ms, _ = timed_region(True)
     trk.cell.finish()
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     total_ms = max_over_ranks(sum(step_ms), dev)
     value = B_total * T * args.steps / (total_ms / 1e3)
 
@@ -376,7 +391,7 @@ def main():
     abytes = algorithmic_bytes_per_seqstep(kw)
     if training:    # + HBM spill of the history (write forward, read backward), SURVEY.md s8d
         abytes += 2 * (kw["mem_size"] * kw["mem_dim"] + (kw["read_head_size"] + kw["write_head_size"]) * kw["mem_size"]) * 4
-    seq_avg_ms = sum(seq_ms) / len(seq_ms)
+    seq_avg_ms = max(sum(seq_ms) / len(seq_ms), 1e-9)
     achieved = abytes * B_local * T / (seq_avg_ms / 1e3) / 1e9
     info = _cabi.last_launch_info()
     streaming = bool(info.get("streaming")) and stream_ms and stream_ms[-1]["steps"] > 0 and not training
@@ -391,7 +406,8 @@ def main():
         "kernel": "ntm_seq_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_seq_step": abytes, "kernel_ms": seq_avg_ms,
-        "kernel_share_of_step": seq_avg_ms / (sum(step_ms) / len(step_ms)),
+        "kernel_share_of_step": seq_avg_ms / (sum(prof_step_ms) / len(prof_step_ms)),
+        "profiled_ms_per_step": sum(prof_step_ms) / len(prof_step_ms),
         "xproj_ms": sum(xp_ms) / len(xp_ms),
         "note": "state is shared-memory resident, so the level that actually bounds the fused step is "
                 "SMEM/FP32, not HBM: see smem_*",
@@ -402,15 +418,15 @@ def main():
         # streaming mode: the dominant kernel is the fused addressing/memory kernel, launched once per
         # timestep for the rank's B_local sequences; it IS bound by HBM (M is read and written per step)
         n = len(stream_ms)
-        mem_launch_ms = sum(m["memory"] for m in stream_ms) / n / T
+        mem_launch_ms = max(sum(m["memory"] for m in stream_ms) / n / T, 1e-9)
         achieved = abytes * B_local / (mem_launch_ms / 1e3) / 1e9
-        step_avg = sum(step_ms) / len(step_ms)
+        step_avg = sum(prof_step_ms) / len(prof_step_ms)
         roofline = {
             "kernel": "mem_step_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_seq_step": abytes, "units_per_launch": B_local,
             "kernel_ms": mem_launch_ms, "launches_per_step": T, "ctas_per_sm": info.get("ctas_per_sm"),
-            "kernel_share_of_step": mem_launch_ms * T / step_avg,
+            "kernel_share_of_step": mem_launch_ms * T / step_avg, "profiled_ms_per_step": step_avg,
             "controller_gemm_lstm_ms_per_step": sum(m["controller"] for m in stream_ms) / n,
             "head_param_gemm_ms_per_step": sum(m["head_params"] for m in stream_ms) / n,
             "memory_kernel_ms_per_step": mem_launch_ms * T,
