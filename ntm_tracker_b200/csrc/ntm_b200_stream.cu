@@ -66,7 +66,7 @@ struct MemArgs {
   int oK, oE, oA, oSim, oWg, oWn, oSm, oX;   // shared-memory carve-up (floats)
   int WPC;                                   // warps sharing one 8-chunk column group in pass 2
   // TMA-ring kernel: stages of RPS memory rows, NS stages, NCH chunks per pass
-  int RPS, NS, NCH, RP, SPS, rps_shift;      // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = SPS stages
+  int RPS, NS, NCH, RP, SPS, rps_shift, qps_shift;   // qps_shift: log2(2 * NCH) when that is a power of two, else -1      // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = SPS stages
   int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
   int vec_out;                               // read-vector rows are 16-byte aligned
   uint8_t* tilesA; int KAtotA;               // controller-GEMM operand tiles (read vectors at k = r*M + d), or null
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   float* sRed = sPart + NWARP * H;
   const int stage_floats = RPS * M;
   const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
-  const bool hint = a.l2_hints != 0;
+  constexpr bool hint = true;                  // (the no-hint variant measured the same; compiled out to save issue slots)
   // pass 1 brings the rows in and wants them to survive in L2 until pass 2 re-reads them; after that
   // re-read, and for the rewritten rows, the next use is a whole timestep (the other sequences) away
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   // (the division runs on the issuing lane only, ~32 times per sequence; carrying (sequence, use) pairs
   // instead costs registers this kernel does not have: it spilled and ran 11 % slower)
   auto issue_load = [&](int Qg) {
-    const int si = Qg / QPS, Q = Qg - si * QPS;
+    const int si = a.qps_shift >= 0 ? (Qg >> a.qps_shift) : Qg / QPS, Q = Qg - si * QPS;
     const int j = Q < NCH ? Q : Q - NCH;
     const float* src = a.Min + (size_t)(blockIdx.x + si * G) * a.sMin + (size_t)j * stage_floats;
     uint64_t* fb = bars + (Qg & (NS - 1));
@@ -1388,6 +1388,9 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       ma.rps_shift = 0;
       while ((1 << ma.rps_shift) < ma.RPS) ++ma.rps_shift;
       ma.NCH = N / ma.RPS;
+      ma.qps_shift = -1;
+      for (int sh = 0; sh < 30; ++sh)
+        if ((1 << sh) == 2 * ma.NCH) ma.qps_shift = sh;
       ma.RP = tma_rp(MC);
       ma.SPS = 1;
       ma.oBar = take2(2 * (ma.NS + 1) + 2);

@@ -58,7 +58,8 @@ class LoopNTMTracker(object):
     # Host-resident frames (page-locked torch tensor): the call is cut into blocks of timesteps and the
     # upload of block i+1 (one strided DMA, ntm_b200_copy_frames_h2d) overlaps the kernels of block i; the
     # state is carried from block to block on the device, every sequence stays in every launch, so the
-    # kernels run at full batch.  None = automatic (4 blocks once the frames exceed 64 MB), 1 = off.
+    # kernels run at full batch.  None = automatic (once the frames exceed 64 MB: a short first block, so
+    # that little of the upload is exposed, then blocks of ~16 steps), 1 = off, n = n equal blocks.
     time_blocks = None
 
     def _time_blocks(self, inputs):
@@ -68,8 +69,19 @@ class LoopNTMTracker(object):
         B, T, D = inputs.shape
         n = self.time_blocks
         if n is None:
-            n = 4 if (B * T * D * 4 >= (64 << 20) and T >= 16) else 1
+            n = len(self._auto_bounds(T)) if (B * T * D * 4 >= (64 << 20) and T >= 16) else 1
         return max(1, min(int(n), T))
+
+    @staticmethod
+    def _auto_bounds(T):
+        """[0,4) [4,16) [16,32) ... : only the first 4 steps' upload is not hidden behind kernels."""
+        cuts = [0, min(4, T)]
+        if T > 4:
+            cuts.append(min(16, T))
+        while cuts[-1] < T:
+            cuts.append(min(cuts[-1] + 16, T))
+        cuts = sorted(set(cuts))
+        return list(zip(cuts[:-1], cuts[1:]))
 
     def _call_host_time_pipelined(self, xh, state, n):
         import ctypes as C
@@ -77,7 +89,8 @@ class LoopNTMTracker(object):
         cell, dev = self.cell, self.cell.device
         lib = _cabi.load()
         B, T, D = xh.shape
-        bounds = [(i * T // n, (i + 1) * T // n) for i in range(n)]
+        bounds = self._auto_bounds(T) if self.time_blocks is None else \
+            [(i * T // n, (i + 1) * T // n) for i in range(n)]
         compute = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
         copy.wait_stream(compute)
