@@ -8,10 +8,13 @@
 //   activations, batched_smooth_cosine_similarity, content focus, gate, batched_circular_convolution,
 //   sharpening, erase/add write, read ....... ntm_cell.py:133-215, ops.py:135-242 -> mem_step_kernel
 //
-// mem_step_kernel is the HBM-bound kernel of this mode: one CTA per sequence-step.  Pass 1 streams the
-// sequence's N x M memory from HBM (similarities), the addressing runs in shared memory, pass 2 streams
-// the memory again -- out of L2, where pass 1 just put it -- and writes M' back: one HBM read and one
-// HBM write of M per sequence-step instead of the three passes of the algorithmic count.
+// The HBM-bound kernel of this mode is the fused addressing / memory kernel, in two variants:
+//   mem_step_tma_kernel  persistent CTAs, the sequence's rows stream through a shared-memory ring of bulk
+//                        TMA copies (the fast path: M <= 512, N a multiple of the pass-2 iteration);
+//   mem_step_kernel      one CTA per sequence-step, register-streamed ld.global (any M % 4 == 0).
+// Both make two passes over the N x M memory -- pass 1 from HBM (similarities), the addressing in shared
+// memory, pass 2 out of L2, where pass 1 just put the rows, writing M' back: one HBM read and one HBM
+// write of M per sequence-step instead of the three passes of the algorithmic count.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -66,12 +69,12 @@ struct MemArgs {
   int oK, oE, oA, oSim, oWg, oWn, oSm, oX;   // shared-memory carve-up (floats)
   int WPC;                                   // warps sharing one 8-chunk column group in pass 2
   // TMA-ring kernel: stages of RPS memory rows, NS stages, NCH chunks per pass
-  int RPS, NS, NCH, RP, SPS, rps_shift, qps_shift;   // qps_shift: log2(2 * NCH) when that is a power of two, else -1      // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = SPS stages
+  int RPS, NS, NCH, RP, qps_shift;           // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = two stages;
+                                             // qps_shift: log2(2 * NCH) when that is a power of two, else -1
   int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
   int vec_out;                               // read-vector rows are 16-byte aligned
   uint8_t* tilesA; int KAtotA;               // controller-GEMM operand tiles (read vectors at k = r*M + d), or null
   long long B;
-  int l2_hints;
   long long* prof;                           // [B][8] phase timestamps (globaltimer ns) of the last launch, or null
 };
 
@@ -470,23 +473,6 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes, uint64_t pol, bool hint) {
-  if (hint)
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
-                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes), "l"(pol) : "memory");
-  else
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_nc(void* dst, const void* src, uint32_t bytes, uint64_t pol, bool hint) {
-  if (hint)
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
-                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes), "l"(pol) : "memory");
-  else
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
-                 ::"l"(dst), "r"(s_u32(src)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void st_global_hint(float* p, const float4 v, uint64_t pol, bool hint) {
   if (hint)
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n"
@@ -494,16 +480,12 @@ __device__ __forceinline__ void st_global_hint(float* p, const float4 v, uint64_
   else
     __stcg(reinterpret_cast<float4*>(p), v);
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ long long gtimer() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 #define MEM_PROF(slot) do { if (a.prof != nullptr && tid == 0) a.prof[(size_t)b * 16 + (slot)] = gtimer(); } while (0)
-template <int NKEEP>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NKEEP) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
@@ -824,7 +806,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     if (tid == 0 && si + 1 < nseq) issue_params(si + 1);
 
     // ---- pass 2: thread -> (16-byte column chunk c, quad slot rp); per iteration the CTA reads RP quads
-    //      of four consecutive rows (= SPS whole stages) from the ring and writes M' straight to HBM ----
+    //      of four consecutive rows (= two whole stages) from the ring and writes M' straight to HBM ----
     float4 racc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1114,14 +1096,7 @@ cudaError_t launch_mem_v(const MemArgs& a, long long B, int smem, cudaStream_t s
 }
 template <int R, int W>
 cudaError_t launch_mem_rw(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
-#ifdef NTM_EXP_MEM_VARIANTS
-  if constexpr (R == 4 && W == 1) {
-    static const int v = getenv("NTM_B200_MEM_VARIANT") ? atoi(getenv("NTM_B200_MEM_VARIANT")) : 0;
-    if (v == 1) return launch_mem_v<R, W, 256, 2>(a, B, smem, stream);
-    if (v == 2) return launch_mem_v<R, W, 256, 3>(a, B, smem, stream);
-  }
-#endif
-  return launch_mem_v<R, W, MEM_NT, 1>(a, B, smem, stream);
+  return launch_mem_v<R, W, MEM_NT, 2>(a, B, smem, stream);   // 2 CTAs/SM: 720 us per C3 step vs 1073 (1/SM) and 796 (3/SM)
 }
 template <int R>
 cudaError_t launch_mem_r(int W, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
@@ -1385,20 +1360,16 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       ma.oSm = take2(4 * H + H * SMAX + (TMA_NT / 32) * H + 3 * H * std::max(1, (TMA_NT / 32) / H) + 8);
       ma.NS = TMA_NS;
       ma.RPS = tma_rps(N, M);
-      ma.rps_shift = 0;
-      while ((1 << ma.rps_shift) < ma.RPS) ++ma.rps_shift;
       ma.NCH = N / ma.RPS;
       ma.qps_shift = -1;
       for (int sh = 0; sh < 30; ++sh)
         if ((1 << sh) == 2 * ma.NCH) ma.qps_shift = sh;
       ma.RP = tma_rp(MC);
-      ma.SPS = 1;
       ma.oBar = take2(2 * (ma.NS + 1) + 2);
       o2 = round_up(o2, 32);                      // 128-byte aligned ring
       ma.oRing = o2;
       o2 += ma.NS * ma.RPS * M;
       smem_tma = 4 * o2;
-      ma.l2_hints = getenv("NTM_B200_NO_L2_HINTS") == nullptr ? 1 : 0;
     }
     ma.N = N; ma.M = M; ma.M4 = M4; ma.MC = MC; ma.Npad = Npad; ma.S = S;
     ma.shift0 = -((S + 1) / 2);   // Python-2 floor(-S/2), ops.py:204

@@ -130,3 +130,50 @@ def test_variable_names_match_reference_source(golden_dir):
     cell = NTMCell(3, mem_size=16, mem_dim=8, controller_hidden_size=12, controller_num_layers=2,
                    write_head_size=1, read_head_size=2)
     assert cell.variable_shapes(5) == O.param_shapes(s)
+
+
+def test_workspace_covers_the_streaming_mode(lib):
+    """ntm_b200_query sizes the workspace for whichever mode the call will pick: for a large batch it
+    must hold the streaming mode's buffers (hoisted projection [B,T,4C], activation rows, K-slice slabs,
+    head-parameter rows, operand tiles), and it grows monotonically with the batch."""
+    prev = 0
+    for B in (64, 512, 4096):
+        st, plan = query(lib, shape(), B, 64)
+        assert st == 0
+        xw = B * 64 * 800 * 4                       # hoisted projection alone
+        slabs = 5 * B * 800 * 4                     # K-slice partials of the controller GEMM
+        tiles = ((B + 127) // 128) * 36 * 32768     # bf16 hi/lo operand records, K = 2248 -> 36 atoms
+        assert plan.workspace_bytes >= xw + slabs + tiles
+        assert plan.workspace_bytes > prev
+        prev = plan.workspace_bytes
+
+
+def test_copy_frames_argument_checks(lib):
+    """ntm_b200_copy_frames_h2d: null pointers and bad step ranges are rejected before any CUDA call;
+    with valid arguments a machine without an sm_100 device answers NO_DEVICE (no CPU path)."""
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.ntm_b200_copy_frames_h2d(None, p, 1, 4, 4, 0, 2, None) == 3
+    assert lib.ntm_b200_copy_frames_h2d(p, p, 1, 4, 4, 2, 2, None) == 1      # empty range
+    assert lib.ntm_b200_copy_frames_h2d(p, p, 1, 4, 4, 0, 5, None) == 1      # beyond T
+    assert lib.ntm_b200_copy_frames_h2d(p, p, 0, 4, 4, 0, 2, None) == 1
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.ntm_b200_copy_frames_h2d(p, p, 1, 4, 4, 0, 2, None) == 7
+
+
+def test_time_block_bounds_cover_every_step():
+    """Host pipeline of LoopNTMTracker: the automatic blocks are a partition of [0, T) with a short
+    first block (only its upload is exposed)."""
+    from ntm_tracker_b200 import LoopNTMTracker
+    for T in (1, 3, 4, 5, 16, 17, 32, 64, 100):
+        b = LoopNTMTracker._auto_bounds(T)
+        assert b[0][0] == 0 and b[-1][1] == T
+        assert all(lo < hi for lo, hi in b) and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert b[0][1] - b[0][0] <= 4
+
+
+def test_stream_profiling_hooks_answer_without_a_call(lib):
+    """The streaming-mode measurement hooks are safe to call when no streaming call ran on this thread."""
+    assert _cabi.last_stream_ms()["steps"] == 0
+    assert _cabi.stream_phase_ns()["ctas"] == 0
