@@ -14,7 +14,8 @@
 //
 // One persistent CTA per SM owns one (128-column weight tile, K-slice of KA atoms): weight hi half
 // resident in TMEM (A-from-TMEM MMAs), lo half resident in shared memory.  Roles:
-//   warp 0      producer: one 32 KiB cp.async.bulk per (row block, K atom) into a 3-slot ring
+//   warp 0      producer: one 32 KiB cp.async.bulk per (row block, K atom) into a ring of 3 slots (7 when the
+//               K slice is <= 256 wide: then the weight lo half lives in TMEM as well and shared memory is all ring)
 //   warp 1      tcgen05.mma issuer (one elected lane); commits release ring slots / publish accumulators
 //   warps 2..5  epilogue: TMEM -> registers -> global, double-buffered against the next row block's MMAs
 #pragma once
@@ -28,7 +29,8 @@ namespace ntm_b200 {
 namespace gemmws {
 
 constexpr int KA_MAX = 8;            // K atoms (64 wide) per slice: 256 TMEM columns of weight hi halves
-constexpr int NSLOT = 3;             // activation ring slots (32 KiB each)
+constexpr int NSLOT_MAX = 7;         // activation ring slots (32 KiB each): 3 next to a resident weight lo half in
+                                     // shared memory, 7 when both weight halves fit TMEM (K slice <= 256)
 constexpr int THREADS = 192;
 constexpr int ATOM_BYTES = 16384;    // [128 rows][128 B]
 constexpr int REC_BYTES = 2 * ATOM_BYTES;
@@ -41,6 +43,8 @@ struct Args {
   float* out;            // slab ks at out + ks * slab, rows ldo apart
   long long rows, slab;
   int ldo, ncols, ntiles, kslices, ngroups, KAtot, KA;
+  int nslot;             // ring slots
+  int wlo_tmem;          // 1: weight lo half in TMEM too (KA <= 4; `wlo` then holds packed words like `whi`)
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -64,10 +68,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
   const int group = blockIdx.x / (a.ntiles * a.kslices);
   const int ka0 = ks * a.KA;
   const int nka = min(a.KA, a.KAtot - ka0);           // atoms of this slice
-  uint8_t* sWlo = smem;                                // [KA][16 KiB]
-  uint8_t* sRing = smem + (size_t)a.KA * ATOM_BYTES;   // [NSLOT][hi | lo]
+  const int NSLOT = a.nslot;
+  uint8_t* sWlo = smem;                                // [KA][16 KiB] (absent when the lo half lives in TMEM)
+  uint8_t* sRing = smem + (a.wlo_tmem ? 0 : (size_t)a.KA * ATOM_BYTES);   // [NSLOT][hi | lo]
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT], acc_full[2], acc_empty[2], wbar, whibar;
+  __shared__ __align__(8) uint64_t full[NSLOT_MAX], empty[NSLOT_MAX], acc_full[2], acc_empty[2], wbar, whibar;
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -81,15 +86,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t tWhi = tmem + 256;                    // accumulators: columns 0..127 and 128..255
+  const uint32_t tWlo = tWhi + 128;                    // (wlo_tmem: KA <= 4, so each half takes <= 128 columns)
   const long long nrb = (a.rows + 127) / 128;
   const size_t wrec = (size_t)tile * a.kslices + ks;   // this CTA's weight record
 
   if (warp == 0) {
     // ------------------------------------------------ producer ------------------------------------
     if (lane == 0) {
-      mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
-      for (int k = 0; k < nka; ++k)
-        bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
+      if (!a.wlo_tmem) {
+        mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
+        for (int k = 0; k < nka; ++k)
+          bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
+      }
       uint32_t use = 0;
       for (long long rb = group; rb < nrb; rb += a.ngroups) {
         for (int k = 0; k < nka; ++k, ++use) {
@@ -105,8 +113,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
     // ------------------------------------------------ MMA issuer ----------------------------------
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16_f32(128, 128);
-      mbar_wait(&wbar, 0);       // weight lo half in shared memory (bulk copies)
-      mbar_wait(&whibar, 0);     // weight hi half in TMEM (stored by the four epilogue warps)
+      if (!a.wlo_tmem) mbar_wait(&wbar, 0);   // weight lo half in shared memory (bulk copies)
+      mbar_wait(&whibar, 0);     // weight hi (and lo) half in TMEM (stored by the four epilogue warps)
       tcgen05_fence_after();
       uint32_t use = 0, it = 0;
       for (long long rb = group; rb < nrb; rb += a.ngroups, ++it) {
@@ -128,7 +136,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
             const uint32_t tA = tWhi + (uint32_t)(k * 64 + s * 16) / 2;
             mma_ts(tAcc, tA, dBhi, idesc, (k == 0 && s == 0) ? 0u : 1u);
             mma_ts(tAcc, tA, dBlo, idesc, 1u);
-            mma_ss(tAcc, dWlo, dBhi, idesc, 1u);
+            if (a.wlo_tmem) mma_ts(tAcc, tWlo + (uint32_t)(k * 64 + s * 16) / 2, dBhi, idesc, 1u);
+            else mma_ss(tAcc, dWlo, dBhi, idesc, 1u);
           }
           mma_commit(&empty[slot]);                                // slot reusable once these MMAs have read it
         }
@@ -150,6 +159,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
         const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
         tmem_st_x8(tWhi + lane_addr + q * 8, v);
       }
+      if (a.wlo_tmem) {
+        const uint32_t* srl = reinterpret_cast<const uint32_t*>(a.wlo) + (wrec * 128 + jl) * (size_t)(a.KA * 32);
+        for (int q = 0; q < nka * 4; ++q) {
+          const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(srl + q * 8));
+          const uint4 hi4 = __ldg(reinterpret_cast<const uint4*>(srl + q * 8 + 4));
+          const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+          tmem_st_x8(tWlo + lane_addr + q * 8, v);
+        }
+      }
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
@@ -164,16 +182,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
       tcgen05_fence_after();
       const long long r0 = rb * 128;
       const uint32_t tAcc = tmem + ab * 128 + lane_addr;
+      // two 32-column loads in flight per wait (a tcgen05.ld queues behind the MMAs of the next row block,
+      // so round trips, not bytes, are what the epilogue pays for)
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tAcc + c0, v);
+      for (int c0 = 0; c0 < 128; c0 += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(tAcc + c0, v0);
+        tmem_ld_x32(tAcc + c0 + 32, v1);
         tmem_wait_ld();
         if (jcol < a.ncols) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < 32; ++e) {
             const long long r = r0 + c0 + e;
-            if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v[e]) + bias;
+            if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v0[e]) + bias;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const long long r = r0 + c0 + 32 + e;
+            if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v1[e]) + bias;
           }
         }
       }
@@ -236,7 +262,7 @@ __global__ void pack_act_tiles_kernel(const float* __restrict__ x, long long row
 
 // W [K, ncols] (row stride ldw) -> per (tile, slice): hi words [128 cols][KA*32], lo swizzled images [KA][16 KiB].
 __global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int K, int ncols, int ldw, uint32_t* whi,
-                                         uint8_t* wlo, int ntiles, int kslices, int KA) {
+                                         uint8_t* wlo, int ntiles, int kslices, int KA, int wlo_words) {
   const long long total = (long long)ntiles * kslices * 128 * KA * 8;      // 8-k chunks
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int jl = (int)(i & 127);                   // column fastest: coalesced reads of W rows
@@ -257,14 +283,18 @@ __global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int K, int
     umma::split_pack_bf16(v[6], v[7], h.w, l.w);
     const size_t wrec = (size_t)tile * kslices + ks;
     *reinterpret_cast<uint4*>(whi + (wrec * 128 + jl) * (size_t)(KA * 32) + ch * 4) = h;
-    uint8_t* img = wlo + (wrec * KA + (kl >> 6)) * ATOM_BYTES +
-                   (jl >> 3) * 1024 + (jl & 7) * 128 + ((((kl & 63) >> 3) ^ (jl & 7)) << 4);
-    *reinterpret_cast<uint4*>(img) = l;
+    if (wlo_words) {   // lo half destined for TMEM: same packed-word layout as the hi half
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(wlo) + (wrec * 128 + jl) * (size_t)(KA * 32) + ch * 4) = l;
+    } else {
+      uint8_t* img = wlo + (wrec * KA + (kl >> 6)) * ATOM_BYTES +
+                     (jl >> 3) * 1024 + (jl & 7) * 128 + ((((kl & 63) >> 3) ^ (jl & 7)) << 4);
+      *reinterpret_cast<uint4*>(img) = l;
+    }
   }
 }
 
 struct Plan {
-  int K, ncols, KAtot, KA, kslices, ntiles, ngroups;
+  int K, ncols, KAtot, KA, kslices, ntiles, ngroups, nslot, wlo_tmem;
   size_t whi_bytes, wlo_bytes, act_bytes;
 };
 inline Plan make_plan(int K, int ncols, long long rows, int nsm) {
@@ -281,6 +311,8 @@ inline Plan make_plan(int K, int ncols, long long rows, int nsm) {
   if (g > nrb) g = nrb;
   if (g < 1) g = 1;
   p.ngroups = (int)g;
+  p.wlo_tmem = (p.KA <= 4) ? 1 : 0;                  // hi + lo halves: 2 * KA * 32 <= 256 TMEM columns
+  p.nslot = p.wlo_tmem ? NSLOT_MAX : 3;
   p.whi_bytes = (size_t)units * 128 * p.KA * 32 * 4;
   p.wlo_bytes = (size_t)units * p.KA * ATOM_BYTES;
   p.act_bytes = (size_t)nrb * p.KAtot * REC_BYTES;
@@ -288,13 +320,14 @@ inline Plan make_plan(int K, int ncols, long long rows, int nsm) {
 }
 inline bool plan_ok(const Plan& p, int nsm) { return p.ntiles * p.kslices <= nsm && p.KA <= KA_MAX; }
 
-inline int smem_bytes(const Plan& p) { return 1024 + p.KA * ATOM_BYTES + NSLOT * REC_BYTES; }
+inline int smem_bytes(const Plan& p) { return 1024 + (p.wlo_tmem ? 0 : p.KA * ATOM_BYTES) + p.nslot * REC_BYTES; }
 
 inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi, const uint8_t* wlo, const float* bias,
                           float* out, int ldo, long long slab, long long rows, cudaStream_t stream) {
   Args a{};
   a.act = act; a.whi = whi; a.wlo = wlo; a.bias = bias; a.out = out; a.rows = rows; a.slab = slab; a.ldo = ldo;
   a.ncols = p.ncols; a.ntiles = p.ntiles; a.kslices = p.kslices; a.ngroups = p.ngroups; a.KAtot = p.KAtot; a.KA = p.KA;
+  a.nslot = p.nslot; a.wlo_tmem = p.wlo_tmem;
   const int smem = smem_bytes(p);
   static int configured = 0;
   if (configured < smem) {

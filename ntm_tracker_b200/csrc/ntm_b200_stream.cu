@@ -1326,9 +1326,9 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     gemmws::pack_act_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(act[0] + RM, B, C, ws.actK[0], tilesA, planA.KAtot, RM);
     gemmws::pack_act_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(act[0] + RM, B, C, ws.actK[0], tilesC, planC.KAtot, 0);
     gemmws::pack_weight_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(w->lstm_w[0] + (size_t)s->input_dim * 4 * C, ws.actK[0],
-                                                                4 * C, 4 * C, whiA, wloA, planA.ntiles, planA.kslices, planA.KA);
+                                                                4 * C, 4 * C, whiA, wloA, planA.ntiles, planA.kslices, planA.KA, planA.wlo_tmem);
     gemmws::pack_weight_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(wC, C, PO4, PO4, whiC, wloC, planC.ntiles, planC.kslices,
-                                                                planC.KA);
+                                                                planC.KA, planC.wlo_tmem);
     for (int i = 0; i < 5; ++i) count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "gemmws pack kernels");
   }
