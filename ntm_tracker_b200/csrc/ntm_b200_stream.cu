@@ -1052,9 +1052,24 @@ __global__ void lstm_stream_kernel(const LstmArgs a) {
   for (int q = 0; q < 4; ++q) {
     const int col = q * C + u;
     float v = (a.l == 0) ? __ldg(a.xw + (b * a.T + a.t) * (long long)(4 * C) + col) : __ldg(a.bias + col);
-    for (int ks = 0; ks < a.KS; ++ks) v += __ldcg(a.part + (size_t)ks * a.slab + b * (long long)(4 * C) + col);
     z[q] = v;
-    if (a.hZ && live) a.hZ[((((size_t)a.t * a.B + b) * a.L + a.l) * 4 + q) * C + u] = v;
+  }
+  // K-slice partials of the controller GEMM, summed in slice order (deterministic); the loads of a slice
+  // for all four gates are issued together
+  {
+    const float* pp = a.part + b * (long long)(4 * C) + u;
+#pragma unroll 4
+    for (int ks = 0; ks < a.KS; ++ks) {
+      float sl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sl[q] = __ldcg(pp + (size_t)ks * a.slab + q * C);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) z[q] += sl[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (a.hZ && live) a.hZ[((((size_t)a.t * a.B + b) * a.L + a.l) * 4 + q) * C + u] = z[q];
   }
   float* cp = a.ctrl + b * a.sctrl + (2 * a.l) * C + u;
   const float c_prev = *cp;
