@@ -98,14 +98,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
         for (int k = 0; k < nka; ++k)
           bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
       }
-      uint32_t use = 0;
+      uint32_t slot = 0, phase = 0;      // ring position kept incrementally (no division on this thread's path)
       for (long long rb = group; rb < nrb; rb += a.ngroups) {
-        for (int k = 0; k < nka; ++k, ++use) {
-          const uint32_t slot = use % NSLOT;
-          mbar_wait(&empty[slot], ((use / NSLOT) & 1u) ^ 1u);      // passes on a fresh barrier
+        for (int k = 0; k < nka; ++k) {
+          mbar_wait(&empty[slot], phase ^ 1u);                     // passes on a fresh barrier
           mbar_expect_tx(&full[slot], REC_BYTES);
           bulk_g2s(sRing + (size_t)slot * REC_BYTES, a.act + ((size_t)rb * a.KAtot + ka0 + k) * REC_BYTES, REC_BYTES,
                    &full[slot]);
+          if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
         }
       }
     }
@@ -116,15 +116,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
       if (!a.wlo_tmem) mbar_wait(&wbar, 0);   // weight lo half in shared memory (bulk copies)
       mbar_wait(&whibar, 0);     // weight hi (and lo) half in TMEM (stored by the four epilogue warps)
       tcgen05_fence_after();
-      uint32_t use = 0, it = 0;
+      uint32_t slot = 0, phase = 0, it = 0;
       for (long long rb = group; rb < nrb; rb += a.ngroups, ++it) {
         const uint32_t ab = it & 1u;
         mbar_wait(&acc_empty[ab], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tAcc = tmem + ab * 128;
-        for (int k = 0; k < nka; ++k, ++use) {
-          const uint32_t slot = use % NSLOT;
-          mbar_wait(&full[slot], (use / NSLOT) & 1u);
+        for (int k = 0; k < nka; ++k) {
+          mbar_wait(&full[slot], phase);
           tcgen05_fence_after();
           const uint8_t* sBhi = sRing + (size_t)slot * REC_BYTES;
           const uint8_t* sBlo = sBhi + ATOM_BYTES;
@@ -140,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
             else mma_ss(tAcc, dWlo, dBhi, idesc, 1u);
           }
           mma_commit(&empty[slot]);                                // slot reusable once these MMAs have read it
+          if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
         }
         mma_commit(&acc_full[ab]);
       }
@@ -182,24 +182,42 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
       tcgen05_fence_after();
       const long long r0 = rb * 128;
       const uint32_t tAcc = tmem + ab * 128 + lane_addr;
-      // two 32-column loads in flight per wait (a tcgen05.ld queues behind the MMAs of the next row block,
-      // so round trips, not bytes, are what the epilogue pays for)
+      if (a.wlo_tmem) {
+        // short K (few MMAs per row block): the epilogue is on the critical path, and a tcgen05.ld queues
+        // behind the MMAs of the next row block -- two 32-column loads in flight per wait (38.5 vs 42 us at C3)
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 64) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_x32(tAcc + c0, v0);
-        tmem_ld_x32(tAcc + c0 + 32, v1);
-        tmem_wait_ld();
-        if (jcol < a.ncols) {
+        for (int c0 = 0; c0 < 128; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_x32(tAcc + c0, v0);
+          tmem_ld_x32(tAcc + c0 + 32, v1);
+          tmem_wait_ld();
+          if (jcol < a.ncols) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const long long r = r0 + c0 + e;
-            if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v0[e]) + bias;
+            for (int e = 0; e < 32; ++e) {
+              const long long r = r0 + c0 + e;
+              if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v0[e]) + bias;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const long long r = r0 + c0 + 32 + e;
+              if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v1[e]) + bias;
+            }
           }
+        }
+      } else {
+        // long K: the epilogue hides behind the next row block's MMAs; narrow loads disturb their
+        // A-from-TMEM operand reads least (57 vs 64 us at C3 with the wide ones)
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(tAcc + c0, v);
+          tmem_wait_ld();
+          if (jcol < a.ncols) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const long long r = r0 + c0 + 32 + e;
-            if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v1[e]) + bias;
+            for (int e = 0; e < 16; ++e) {
+              const long long r = r0 + c0 + e;
+              if (r < a.rows) outp[r * a.ldo] = __uint_as_float(v[e]) + bias;
+            }
           }
         }
       }

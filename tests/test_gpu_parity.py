@@ -408,3 +408,19 @@ def test_time_blocked_host_call_matches_device_call():
         assert maxerr(to_np(trk.final_state[k]), st_d[k]) <= 1e-5, k
     ro, rl, rs = O.run_sequence(params, s, x)
     assert maxerr(to_np(log_h), rl) <= TOL and maxerr(to_np(trk.final_state["M"]), rs["M"]) <= TOL
+
+
+@pytest.mark.parametrize("switch", ["NTM_B200_NO_TMA_RING", "NTM_B200_OLD_GEMM"])
+def test_streaming_fallback_kernels(gemm_path, switch):
+    """The streaming mode's generic kernels (register-streamed memory kernel; split-K tile GEMM with
+    in-kernel operand conversion) serve the shapes the fast kernels do not cover.  Forced here on a shape
+    the fast kernels DO cover, so that both families are held to the same oracle."""
+    if gemm_path != "stream":
+        pytest.skip("streaming mode only")
+    os.environ[switch] = "1"
+    try:
+        kw, _, _ = O.CONFIGS["c2_tracker"]
+        errs, _, _ = run_vs_oracle(O.NTMShape(**kw), 70, 5, 91)
+    finally:
+        os.environ.pop(switch, None)
+    assert max(errs.values()) <= TOL, errs
