@@ -14,6 +14,17 @@ from oracle.ntm_ref_torch import TorchRefNTM  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["resident", "stream"])
+def forward_mode(request):
+    """Every training test runs with both forward implementations recording the history: the persistent
+    resident kernel and the streaming mode (where pass 2 of step t writes straight into slot t+1 of the
+    recorded memories); shapes the streaming kernels do not cover fall back to the resident kernel."""
+    import os
+    os.environ["NTM_B200_MODE"] = request.param
+    yield request.param
+    os.environ.pop("NTM_B200_MODE", None)
+
+
 def reference_grads(s, params, x, gather, targets):
     ref = TorchRefNTM(s, params, dtype=torch.float64, requires_grad=True)
     _, logits, _ = ref.run(torch.from_numpy(x))
