@@ -438,14 +438,17 @@ __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------
-// TMA-ring variant of the memory kernel (the fast path: M <= 512 columns per 128 threads, H*CPL <= 20).
-// Same arithmetic as mem_step_kernel; what changes is how the memory moves.  The sequence's N x M rows
-// are contiguous in HBM, so they stream through a ring of NS shared-memory stages (RPS rows each) with
-// 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): the copies are issued before the activations
-// run, pass 1 consumes a stage per warp (keys in registers) and refills it itself, the tail of pass 1
-// already prefetches the head of pass 2 (out of L2) behind the addressing phase, and pass 2 updates a
-// stage in place and hands it to a bulk store.  Bytes in flight per CTA = the ring, independent of
-// registers and occupancy -- which is what an HBM-latency-bound stream needs.
+// TMA-ring variant of the memory kernel (the fast path: M <= 512, H * ceil(M / 128) <= 20, N a multiple of
+// the rows of a pass-2 iteration).  Same arithmetic as mem_step_kernel; what changes is how the memory
+// moves.  The sequence's N x M rows are contiguous in HBM, so they stream through a ring of NS = 8
+// shared-memory stages (RPS rows = 8 KiB each) with 1-D bulk copies (cp.async.bulk + mbarrier
+// complete_tx).  CTAs are persistent (2 per SM) and the ring never drains: stage uses are numbered over
+// all the sequences of a CTA, whoever releases use Q issues the load of use Q + NS, so the tail of pass 1
+// prefetches the head of pass 2 (out of L2) behind the addressing phase and the tail of pass 2 prefetches
+// the next sequence's pass 1 (from HBM) -- together with its head parameters, weightings and column norms
+// -- behind finalize / activations.  Pass 1 is consumed by four two-warp teams that own two slots each
+// (keys in registers); pass 2 reads the ring and stores M' straight to HBM.  Bytes in flight per CTA = the
+// ring, independent of registers and occupancy -- which is what an HBM-latency-bound stream needs.
 constexpr int TMA_NT = 256;
 constexpr int TMA_NS = 8;     // ring stages (one stage = half the rows of a pass-2 iteration, 8 KiB at M*RP = 1024)
 
