@@ -613,17 +613,20 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         for (int h = 0; h < H; ++h) sPart[warp * H + h] = ss[h];
       }
     }
-    if (tid < H) {
-      sBeta[tid] = softplus_f(raw[offBeta + tid]);
-      sG[tid] = sigmoid_f(raw[offG + tid]);
-      sGam[tid] = 1.0f + softplus_f(raw[offGam + tid]);
-      float* sp = sSw + tid * SMAX;
-      float mx = -INFINITY;
-      for (int i = 0; i < S; ++i) { sp[i] = raw[offS + tid * S + i]; mx = fmaxf(mx, sp[i]); }
-      float sum = 0.0f;
-      for (int i = 0; i < S; ++i) { sp[i] = exp_f(sp[i] - mx); sum += sp[i]; }
-      const float rsum = __frcp_rn(sum);
-      for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
+    if (warp < 4 && lane < H) {   // per-head scalars (ntm_cell.py:140,151,161,169): one WARP per quantity (divergent
+      const int h = lane, job = warp;  // branches inside a warp would run one after the other), one lane per head
+      if (job == 0) sBeta[h] = softplus_f(raw[offBeta + h]);
+      else if (job == 1) sG[h] = sigmoid_f(raw[offG + h]);
+      else if (job == 2) sGam[h] = 1.0f + softplus_f(raw[offGam + h]);
+      else {
+        float* sp = sSw + h * SMAX;
+        float mx = -INFINITY;
+        for (int i = 0; i < S; ++i) { sp[i] = raw[offS + h * S + i]; mx = fmaxf(mx, sp[i]); }
+        float sum = 0.0f;
+        for (int i = 0; i < S; ++i) { sp[i] = exp_f(sp[i] - mx); sum += sp[i]; }
+        const float rsum = __frcp_rn(sum);
+        for (int i = 0; i < S; ++i) sp[i] = sp[i] * rsum;
+      }
     }
     if (tid == NT - 1) {   // output projection + softmax (ntm_cell.py:220-221)
       const size_t o = ((size_t)b * a.T + a.t) * a.O;
@@ -720,16 +723,20 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     __syncthreads();
     MEM_PROF(3);
 
-    // ---- addressing (ntm_cell.py:140-176), as in mem_step_kernel but w_prev from shared memory ----
+    // ---- addressing (ntm_cell.py:140-176): one warp (WPH warps when there are spares) per head.  Every
+    //      sweep over the head's N entries handles four entries per lane at a time -- loads, then math,
+    //      then stores -- so the four dependent chains (shared-memory load -> SFU -> store) overlap ----
     {
       constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
       constexpr bool multi = (NWARP / H) > 0;
+      constexpr int U = 4;
       const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
       const int hstep = multi ? H : NWARP;
       float* wout = a.w_out + (size_t)b * a.sw_out;
       for (int h = multi ? hgrp : warp; h < H; h += hstep) {
         float* sh = simS + h * Npad;
         float* gh = wg + h * Npad;
+        const float* wp = wprevS + h * N;
         float* red = sRed + h * 3 * WPH;
         const int nstep = 32 * WPH;
         const int n0 = 32 * sub + lane;
@@ -739,14 +746,19 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         };
         const float gate = sG[h], gamma = sGam[h];
         float kn = 0.0f;
+#pragma unroll
         for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
-        const float rs = 1.0f / sqrtf(fmaxf(kn, 1e-12f));
-        const float beta = sBeta[h];
+        const float scale = sBeta[h] / sqrtf(fmaxf(kn, 1e-12f));   // beta / |k|  (ops.py:152, ntm_cell.py:142)
         float mx = -INFINITY;
-        for (int n = n0; n < N; n += nstep) {
-          const float x = sh[n] * rs * beta;
-          sh[n] = x;
-          mx = fmaxf(mx, x);
+        for (int nb = n0; nb < N; nb += U * nstep) {
+          float x[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) x[u] = (nb + u * nstep < N) ? sh[nb + u * nstep] * scale : -INFINITY;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (nb + u * nstep < N) sh[nb + u * nstep] = x[u];
+            mx = fmaxf(mx, x[u]);
+          }
         }
         mx = warp_max(mx);
         if (WPH > 1) {
@@ -757,10 +769,15 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           for (int i = 1; i < WPH; ++i) mx = fmaxf(mx, red[i]);
         }
         float sum = 0.0f;
-        for (int n = n0; n < N; n += nstep) {
-          const float e = exp_f(sh[n] - mx);
-          sh[n] = e;
-          sum += e;
+        for (int nb = n0; nb < N; nb += U * nstep) {
+          float e[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) e[u] = (nb + u * nstep < N) ? exp_f(sh[nb + u * nstep] - mx) : 0.0f;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (nb + u * nstep < N) sh[nb + u * nstep] = e[u];
+            sum += e[u];
+          }
         }
         sum = warp_sum(sum);
         if (WPH > 1) {
@@ -770,22 +787,39 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
 #pragma unroll
           for (int i = 1; i < WPH; ++i) sum += red[WPH + i];
         }
-        for (int n = n0; n < N; n += nstep) {
-          const float wc = sh[n] / sum;
-          gh[n] = wc * gate + wprevS[h * N + n] * (1.0f - gate);
+        const float gs = gate / sum, g1 = 1.0f - gate;          // w_g = g * softmax + (1 - g) * w_prev
+        for (int nb = n0; nb < N; nb += U * nstep) {
+          float g[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            g[u] = (nb + u * nstep < N) ? fmaf(sh[nb + u * nstep], gs, wp[nb + u * nstep] * g1) : 0.0f;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (nb + u * nstep < N) gh[nb + u * nstep] = g[u];
         }
-        head_bar();
+        head_bar();   // the shift reads neighbours' gated weights
         float psum = 0.0f;
-        for (int n = n0; n < N; n += nstep) {
-          float conv = 0.0f;
-          for (int s = 0; s < S; ++s) {
-            int idx = n + a.shift0 + s;
-            idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
-            conv = fmaf(sSw[h * SMAX + s], gh[idx], conv);
+        for (int nb = n0; nb < N; nb += U * nstep) {
+          float pw[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int n = nb + u * nstep;
+            float conv = 0.0f;
+            if (n < N) {
+              for (int s2 = 0; s2 < S; ++s2) {
+                int idx = n + a.shift0 + s2;   // circular_shift(x, j)[n] = x[(n + j) mod N], ops.py:216-242
+                idx = idx < 0 ? idx + N : (idx >= N ? idx - N : idx);
+                conv = fmaf(sSw[h * SMAX + s2], gh[idx], conv);
+              }
+            }
+            // conv >= 0, gamma >= 1: pow(conv, gamma) on the SFU (lg2 + ex2, ~1e-6 relative); 0 -> 0
+            pw[u] = (n < N) ? exp2f(gamma * __log2f(conv)) : 0.0f;
           }
-          const float pw = exp2f(gamma * log2f(conv));
-          sh[n] = pw;
-          psum += pw;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (nb + u * nstep < N) sh[nb + u * nstep] = pw[u];
+            psum += pw[u];
+          }
         }
         psum = warp_sum(psum);
         if (WPH > 1) {
@@ -795,11 +829,18 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
 #pragma unroll
           for (int i = 1; i < WPH; ++i) psum += red[2 * WPH + i];
         }
-        const float den = psum + 1e-3f;
-        for (int n = n0; n < N; n += nstep) {
-          const float wv = sh[n] / den;
-          wnew[h * Npad + n] = wv;
-          wout[h * N + n] = wv;
+        const float rden = 1.0f / (psum + 1e-3f);   // ntm_cell.py:175-176
+        for (int nb = n0; nb < N; nb += U * nstep) {
+          float wv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) wv[u] = (nb + u * nstep < N) ? sh[nb + u * nstep] * rden : 0.0f;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (nb + u * nstep < N) {
+              wnew[h * Npad + nb + u * nstep] = wv[u];
+              wout[h * N + nb + u * nstep] = wv[u];
+            }
+          }
         }
       }
     }
