@@ -501,14 +501,18 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   return p;
 }
 
-template <int R, int W, int CPL>
+// FULLM: M == 128 * CPL exactly (the tracker and large-memory shapes).  Row stride, stage size and the thread
+// mapping of pass 2 are then compile-time constants: the inner loops lose their address arithmetic and their
+// column-bound checks (the kernel is issue-bound; a third of its instructions were integer / control).
+template <int R, int W, int CPL, bool FULLM>
 __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a) {
   constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32, NS = TMA_NS;
   extern __shared__ float4 mem_smem4[];
   float* smem = reinterpret_cast<float*>(mem_smem4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = a.N, M = a.M, M4 = a.M4, MC = a.MC, Npad = a.Npad, S = a.S;   // here N % 4 == 0: Npad == N
-  const int RPS = a.RPS, NCH = a.NCH;          // RPS: power of two >= 4 that divides N
+  const int N = a.N, Npad = a.Npad, S = a.S;   // here N % 4 == 0: Npad == N
+  const int M = FULLM ? 128 * CPL : a.M, M4 = M, MC = FULLM ? 32 * CPL : a.MC;
+  const int RPS = FULLM ? 2 * (NT / (32 * CPL)) : a.RPS, NCH = a.NCH;   // RPS: power of two >= 4 that divides N
   float* kS = smem + a.oK;      // [H][M4]; after pass 1: partials of the quad slots rp >= 1
   float* eS = smem + a.oE;
   float* aS = smem + a.oA;
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
 
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
             offE = offGam + H, offA = offE + M * W;
-  const int RP = a.RP;                         // pass 2: RP quads of 4 rows per iteration = one stage
+  const int RP = FULLM ? NT / (32 * CPL) : a.RP;   // pass 2: RP quads of 4 rows per iteration = two stages
   const bool worker = tid < RP * MC;
   const int rp = worker ? tid / MC : 0, c = worker ? tid - rp * MC : 0;
 
@@ -1177,17 +1181,17 @@ cudaError_t launch_mem(int R, int W, const MemArgs& a, long long B, int smem, cu
 }
 
 // ---- TMA-ring kernel dispatch ----
-template <int R, int W, int CPL>
+template <int R, int W, int CPL, bool FULLM>
 cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
   if constexpr ((R + W) * CPL > 20) {
     return cudaErrorInvalidValue;
   } else {
     static int configured = 0;
     if (configured < smem) {
-      cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
       configured = smem;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_tma_kernel<R, W, CPL>, TMA_NT, smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_tma_kernel<R, W, CPL, FULLM>, TMA_NT, smem);
       if (g_mem_occ < 1) g_mem_occ = 1;
     }
     int nsm = B200_SMS;
@@ -1196,16 +1200,16 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
     int per_sm = g_mem_occ;
     if (const char* ev = getenv("NTM_B200_MEM_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(ev)));
     const long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
-    mem_step_tma_kernel<R, W, CPL><<<(unsigned)grid, TMA_NT, smem, stream>>>(a);
+    mem_step_tma_kernel<R, W, CPL, FULLM><<<(unsigned)grid, TMA_NT, smem, stream>>>(a);
     return cudaGetLastError();
   }
 }
 template <int R, int W>
 cudaError_t launch_tma_rw(int CPL, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
   switch (CPL) {
-    case 1: return launch_tma_v<R, W, 1>(a, B, smem, stream);
-    case 2: return launch_tma_v<R, W, 2>(a, B, smem, stream);
-    case 4: return launch_tma_v<R, W, 4>(a, B, smem, stream);
+    case 1: return a.M == 128 ? launch_tma_v<R, W, 1, true>(a, B, smem, stream) : launch_tma_v<R, W, 1, false>(a, B, smem, stream);
+    case 2: return a.M == 256 ? launch_tma_v<R, W, 2, true>(a, B, smem, stream) : launch_tma_v<R, W, 2, false>(a, B, smem, stream);
+    case 4: return a.M == 512 ? launch_tma_v<R, W, 4, true>(a, B, smem, stream) : launch_tma_v<R, W, 4, false>(a, B, smem, stream);
   }
   return cudaErrorInvalidValue;
 }
