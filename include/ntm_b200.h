@@ -133,6 +133,16 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
                              float* debug_taps, void* workspace, int64_t workspace_bytes,
                              void* stream);
 
+/* Next block of steps of the sequences the previous ntm_b200_forward_seq call on this thread advanced: same
+ * workspace, batch, shape and packed weights, `state` = that call's state_out, updated in place.  In streaming
+ * mode the per-call initialisation (column norms of the memory, operand packing) is skipped because the
+ * workspace still holds it; in every other case this is an ordinary in-place ntm_b200_forward_seq.  The
+ * reference's counterpart is feeding the fetched state back into the next sess.run (test_tracker.py:284-299). */
+int32_t ntm_b200_forward_seq_continue(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                                      const void* packed, int64_t batch, int64_t steps, const float* inputs,
+                                      const ntm_b200_state* state, float* logits, float* outputs,
+                                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Training-mode history: what the backward pass needs from the forward pass (the reference gets
  * it from TensorFlow's while_loop gradient machinery, `swap_memory=True`,
  * ntm_tracker_new.py:34-40).  Every pointer is an optional caller-owned device buffer:
@@ -247,7 +257,7 @@ int32_t ntm_b200_phase_cycles(const void* workspace, int64_t* out, int32_t max_c
  * resident sequences, CTAs, cluster size, K-slices and K-slice width of the layer-0 controller
  * GEMM, K-slices and K-slice width of the head-parameter GEMM, teams, threads per CTA, CTAs per
  * SM, shared-memory bytes per CTA, x-projection on the tensor path (0/1), execution mode (0 = persistent
- * shared-memory-resident kernel, 1 = streaming), 0...}. */
+ * shared-memory-resident kernel, 1 = streaming), continuation taken (0/1), 0}. */
 int32_t ntm_b200_last_launch_info(int32_t* out16);
 
 /* Number of kernel launches the library has issued in this process (for the

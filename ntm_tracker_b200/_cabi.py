@@ -64,6 +64,9 @@ SYMBOLS = {
                                                C.c_int64, C.c_int64, C.c_void_p, C.POINTER(State),
                                                C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.POINTER(History), C.c_void_p, C.c_int64, C.c_void_p]),
+    "ntm_b200_forward_seq_continue": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p,
+                                                  C.c_int64, C.c_int64, C.c_void_p, C.POINTER(State),
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ntm_b200_memory_backward_step": (C.c_int32, [C.POINTER(Shape), C.c_int64] + [C.c_void_p] * 9),
     "ntm_b200_serialize_tracker_inputs": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -126,7 +129,7 @@ def last_launch_info():
     buf = (C.c_int32 * 16)()
     check(load().ntm_b200_last_launch_info(buf), "last_launch_info")
     keys = ("tensor_path", "sequences_resident", "ctas", "cluster_size", "ks_ctrl", "kw_ctrl", "ks_heads",
-            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta", "xproj_tensor_path", "streaming")
+            "kw_heads", "teams", "threads_per_cta", "ctas_per_sm", "smem_bytes_per_cta", "xproj_tensor_path", "streaming", "continued")
     return dict(zip(keys, list(buf)))
 
 

@@ -445,12 +445,41 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
                                     outputs, debug_taps, nullptr, workspace, workspace_bytes, stream_v);
 }
 
+// What the last streaming call of this thread left valid in its workspace (for ntm_b200_forward_seq_continue).
+struct StreamResume { void* workspace; const float* M; long long batch; ntm_b200_shape shape; const void* packed; };
+static thread_local StreamResume g_resume = {nullptr, nullptr, 0, {}, nullptr};
+
+static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                            const void* packed, int64_t batch, int64_t steps,
+                            const float* inputs, const ntm_b200_state* state_in,
+                            const ntm_b200_state* state_out, float* logits, float* outputs,
+                            float* debug_taps, const ntm_b200_history* history,
+                            void* workspace, int64_t workspace_bytes, void* stream_v, bool want_cont);
+
 int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
                                    const void* packed, int64_t batch, int64_t steps,
                                    const float* inputs, const ntm_b200_state* state_in,
                                    const ntm_b200_state* state_out, float* logits, float* outputs,
                                    float* debug_taps, const ntm_b200_history* history,
                                    void* workspace, int64_t workspace_bytes, void* stream_v) {
+  return forward_impl(shape, weights, packed, batch, steps, inputs, state_in, state_out, logits, outputs, debug_taps,
+                      history, workspace, workspace_bytes, stream_v, false);
+}
+
+int32_t ntm_b200_forward_seq_continue(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                                      const void* packed, int64_t batch, int64_t steps, const float* inputs,
+                                      const ntm_b200_state* state, float* logits, float* outputs,
+                                      void* workspace, int64_t workspace_bytes, void* stream_v) {
+  return forward_impl(shape, weights, packed, batch, steps, inputs, state, state, logits, outputs, nullptr, nullptr,
+                      workspace, workspace_bytes, stream_v, true);
+}
+
+static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
+                            const void* packed, int64_t batch, int64_t steps,
+                            const float* inputs, const ntm_b200_state* state_in,
+                            const ntm_b200_state* state_out, float* logits, float* outputs,
+                            float* debug_taps, const ntm_b200_history* history,
+                            void* workspace, int64_t workspace_bytes, void* stream_v, bool want_cont) {
   if (!shape || !weights || !packed || !inputs || !logits || !workspace) return NTM_B200_ERR_NULL_POINTER;
   int st = check_state(state_in);
   if (st) return st;
@@ -520,9 +549,17 @@ int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_w
     if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync");
     if (prof) cudaEventRecord(g_ev[1], stream);
     const float* wCp = static_cast<const float*>(packed);
+    // continuation: same workspace, batch, shape and packed weights as the last streaming call, and the state
+    // it left (updated in place) -- otherwise this is an ordinary call
+    const bool cont = want_cont && g_resume.workspace == workspace && g_resume.batch == batch &&
+                      g_resume.M == state_in->M && state_in->M == state_out->M && g_resume.packed == packed &&
+                      memcmp(&g_resume.shape, shape, sizeof(*shape)) == 0;
+    g_resume.workspace = nullptr;
     st = stream_forward(shape, weights, wCp, wCp + (size_t)C * hp.PO4, batch, steps, xw, state_in, state_out,
-                        logits, outputs, history, swsb, sws, di.nsm, stream, prof);
+                        logits, outputs, history, swsb, sws, di.nsm, stream, prof, cont);
     if (st) return st;
+    if (history == nullptr) g_resume = StreamResume{workspace, state_out->M, (long long)batch, *shape, packed};
+    g_last_info[14] = cont ? 1 : 0;
     if (prof) {
       cudaEventRecord(g_ev[2], stream);
       g_ev_valid = true;

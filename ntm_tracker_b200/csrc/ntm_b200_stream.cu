@@ -1319,7 +1319,7 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
 int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const float* wC, const float* bC,
                    long long B, long long T, const float* xw, const ntm_b200_state* in,
                    const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
-                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof) {
+                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont) {
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W, S = 2 * s->shift_range + 1;
   const int N = s->mem_size, M = s->mem_dim, M4 = round_up(M, 4), MC = M4 / 4, Npad = round_up(N, 4);
@@ -1348,10 +1348,12 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
   const int WPCi = std::max(1, (INIT_NT / 32) / ncg);
   float* M0 = hM ? hist->M_prev : out->M;                      // memory entering step 0
   const long long sM0 = hM ? (long long)N * M : out->stride_M;
-  init_mem_kernel<<<(unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(in->M, in->stride_M, M0, sM0, cn, N, M, M4, MC, WPCi);
-  count_launch();
-  if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_mem_kernel");
-  {
+  if (!cont) {
+    init_mem_kernel<<<(unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(in->M, in->stride_M, M0, sM0, cn, N, M, M4, MC, WPCi);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_mem_kernel");
+  }
+  if (!cont) {
     SmallInitArgs ia{};
     ia.H = H; ia.N = N; ia.R = R; ia.M = M; ia.C = C; ia.L = L; ia.B = B;
     ia.w_in = in->w; ia.read_in = in->read; ia.ctrl_in = in->controller_state;
@@ -1381,7 +1383,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     planC = gemmws::make_plan(C, PO4, B, nsm);
     ws_ok = gemmws::plan_ok(planA, nsm) && gemmws::plan_ok(planC, nsm);
   }
-  if (ws_ok) {
+  if (ws_ok && !cont) {
     if ((e = cudaMemsetAsync(tilesA, 0, planA.act_bytes, stream)) != cudaSuccess) return set_cuda_error_ext(e, "cudaMemsetAsync");
     if ((e = cudaMemsetAsync(tilesC, 0, planC.act_bytes, stream)) != cudaSuccess) return set_cuda_error_ext(e, "cudaMemsetAsync");
     const int RM = R * M;

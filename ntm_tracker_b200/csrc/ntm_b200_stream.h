@@ -27,12 +27,15 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
 
 // Runs T steps for B sequences.  xw = hoisted x-projection [B,T,4C] (already computed on `stream`),
 // wC/bC = packed [C,PO4] head-parameter + output projection.  Returns an ntm_b200_status.
+// `cont`: continuation of the previous call on this workspace with the state updated in place (in == out):
+// column norms, activation rows, operand tiles and packed weights in the workspace are still valid, so the
+// per-call initialisation is skipped.
 // `hist` (may be null) = training history buffers (ntm_b200.h); in this mode M_prev[t] IS the working
 // memory of step t (pass 2 writes slot t+1), so recording it costs no extra traffic.
 int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const float* wC, const float* bC,
                    long long B, long long T, const float* xw, const ntm_b200_state* in,
                    const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
-                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof);
+                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont = false);
 
 // profiling (after the stream was synchronised): {controller GEMM + LSTM, head-parameter GEMM, memory
 // kernel, init} summed over the T steps, in ms; returns the number of memory-kernel launches (0 = none)

@@ -236,8 +236,11 @@ class NTMCell(object):
         return _cabi.State(*ptrs, *strides), keep
 
     # ------------------------------------------------------------------- run --
-    def _run(self, inputs, state, steps, history=None):
-        """inputs [B, steps, D] float32 CUDA contiguous -> (logits, outputs, new_state, taps)."""
+    def _run(self, inputs, state, steps, history=None, workspace=None, continuation=False):
+        """inputs [B, steps, D] float32 CUDA contiguous -> (logits, outputs, new_state, taps).
+        `workspace`: caller-provided scratch tensor (else cached per geometry).  `continuation`: this call
+        advances the sequences of the previous call on the same workspace; `state` (that call's new_state) is
+        updated in place and returned (ntm_b200_forward_seq_continue)."""
         lib = _cabi.load()
         if not torch.cuda.is_available():
             raise RuntimeError("ntm_tracker_b200 needs a CUDA device (sm_100); there is no CPU fallback")
@@ -259,8 +262,10 @@ class NTMCell(object):
             _cabi.check(lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), self._packed.data_ptr(),
                                                   self._packed.numel(), stream), "pack_weights")
             self._dirty = False
-        ws = self._ws.get((B, T))
+        ws = workspace if workspace is not None else self._ws.get((B, T))
         if ws is None or ws.numel() < plan.workspace_bytes:
+            if workspace is not None:
+                raise ValueError("workspace too small: %d < %d bytes" % (ws.numel(), plan.workspace_bytes))
             ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
             self._ws = {(B, T): ws}                      # keep only the latest geometry
         H, R, N, M = self.num_heads, self.read_head_size, self.mem_size, self.mem_dim
@@ -270,7 +275,12 @@ class NTMCell(object):
         for k, s in want.items():
             if tuple(state[k].shape) != s:
                 raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(state[k].shape), s))
-        new_state = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in want.items()}
+        if continuation:
+            if self.debug or history is not None or any(not state[k].is_contiguous() for k in want):
+                raise ValueError("continuation needs a dense state and neither debug taps nor history")
+            new_state = state
+        else:
+            new_state = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in want.items()}
         sin, keep_in = self._state_struct(state, inner)
         sout, keep_out = self._state_struct(new_state, inner)
         logits = torch.empty(B, T, self.output_dim, dtype=torch.float32, device=dev)
@@ -282,12 +292,18 @@ class NTMCell(object):
         if history is not None:      # training mode: record what the backward pass needs
             hstruct = _cabi.History(*[history[k].data_ptr() if history.get(k) is not None else None
                                       for k, _ in _cabi.History._fields_])
-        _cabi.check(lib.ntm_b200_forward_seq_train(
-            C.byref(shp), C.byref(wts), self._packed.data_ptr(), B, T, inputs.data_ptr(),
-            C.byref(sin), C.byref(sout), logits.data_ptr(), outputs.data_ptr(),
-            taps.data_ptr() if taps is not None else None,
-            C.byref(hstruct) if hstruct is not None else None, ws.data_ptr(), ws.numel(), stream),
-            "forward_seq")
+        if continuation:
+            _cabi.check(lib.ntm_b200_forward_seq_continue(
+                C.byref(shp), C.byref(wts), self._packed.data_ptr(), B, T, inputs.data_ptr(),
+                C.byref(sout), logits.data_ptr(), outputs.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                "forward_seq_continue")
+        else:
+            _cabi.check(lib.ntm_b200_forward_seq_train(
+                C.byref(shp), C.byref(wts), self._packed.data_ptr(), B, T, inputs.data_ptr(),
+                C.byref(sin), C.byref(sout), logits.data_ptr(), outputs.data_ptr(),
+                taps.data_ptr() if taps is not None else None,
+                C.byref(hstruct) if hstruct is not None else None, ws.data_ptr(), ws.numel(), stream),
+                "forward_seq")
         self._last_ws = ws
         return logits, outputs, new_state, taps
 

@@ -74,9 +74,10 @@ class LoopNTMTracker(object):
 
     @staticmethod
     def _auto_bounds(T):
-        """[0,4) [4,16) [16,32) ... : only the first 4 steps' upload is not hidden behind kernels."""
-        cuts = [0, min(4, T)]
-        if T > 4:
+        """[0,2) [2,8) [8,16) [16,32) ... : only the first 2 steps' upload is not hidden behind kernels
+        (blocks after the first are continuations, so short blocks cost next to nothing)."""
+        cuts = [0, min(2, T), min(8, T)]
+        if T > 8:
             cuts.append(min(16, T))
         while cuts[-1] < T:
             cuts.append(min(cuts[-1] + 16, T))
@@ -103,11 +104,18 @@ class LoopNTMTracker(object):
                 ev = torch.cuda.Event()
                 ev.record(copy)
             staged.append((xd, ev))
+        # one workspace for all blocks (sized for the longest), so that every block after the first is a
+        # continuation: state updated in place, column norms / operand tiles / packed weights reused
+        ws_bytes = max(cell.plan(B, t1 - t0)["workspace_bytes"] for t0, t1 in bounds)
+        ws = getattr(self, "_block_ws", None)
+        if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+            ws = self._block_ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)
         outs, logs = [], []
-        for (t0, t1), (xd, ev) in zip(bounds, staged):
+        for i, ((t0, t1), (xd, ev)) in enumerate(zip(bounds, staged)):
             compute.wait_event(ev)
             xd.record_stream(compute)
-            lg, out, state, _ = cell._run(xd, state, t1 - t0)
+            lg, out, state, _ = cell._run(xd, state, t1 - t0, workspace=ws,
+                                          continuation=(i > 0 and not cell.debug))
             outs.append(out); logs.append(lg)
         self.final_state = state
         return torch.cat(outs, 1).cpu(), torch.cat(logs, 1).cpu()

@@ -383,7 +383,7 @@ def test_streaming_mode_is_used(gemm_path):
             assert _cabi.last_launch_info()["streaming"] == want
 
 
-def test_time_blocked_host_call_matches_device_call():
+def test_time_blocked_host_call_matches_device_call(gemm_path):
     """Page-locked host frames: the call is cut into blocks of timesteps whose uploads overlap the
     kernels of the previous block (ntm_b200_copy_frames_h2d + state carried on the device).  Same
     results as the one-shot device-resident call (the column norms are re-derived from the carried
@@ -401,6 +401,9 @@ def test_time_blocked_host_call_matches_device_call():
     xh = torch.from_numpy(x).pin_memory()
     out_h, log_h = trk(xh)
     trk.cell.finish()
+    from ntm_tracker_b200 import _cabi
+    # blocks after the first continue on the same workspace (streaming mode: no re-initialisation)
+    assert _cabi.last_launch_info()["continued"] == (1 if gemm_path == "stream" else 0)
     assert not out_h.is_cuda and tuple(log_h.shape) == (B, T, s.output_dim)
     assert maxerr(to_np(log_h), to_np(log_d)) <= 1e-5
     assert maxerr(to_np(out_h), to_np(out_d)) <= 1e-5
