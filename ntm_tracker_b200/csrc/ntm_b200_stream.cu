@@ -959,15 +959,16 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           const float4 t = *reinterpret_cast<const float4*>(xr + R * M4);
           csq.x += t.x; csq.y += t.y; csq.z += t.z; csq.w += t.w;
         }
-        float* ar = a.act_read + (size_t)b * a.s_act + 4 * c;
+        // fp32 rows for the fallback GEMM (not needed when the next GEMM reads the operand tiles) and for the state
+        float* ar = a.tilesA == nullptr ? a.act_read + (size_t)b * a.s_act + 4 * c : nullptr;
         float* ro = a.read_out != nullptr ? a.read_out + (size_t)b * a.s_read + 4 * c : nullptr;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (a.vec_out) {
-            *reinterpret_cast<float4*>(ar + r * M) = racc[r];
+            if (ar) *reinterpret_cast<float4*>(ar + r * M) = racc[r];
             if (ro) *reinterpret_cast<float4*>(ro + r * M) = racc[r];
           } else {
-            ar[r * M] = racc[r].x; ar[r * M + 1] = racc[r].y; ar[r * M + 2] = racc[r].z; ar[r * M + 3] = racc[r].w;
+            if (ar) { ar[r * M] = racc[r].x; ar[r * M + 1] = racc[r].y; ar[r * M + 2] = racc[r].z; ar[r * M + 3] = racc[r].w; }
             if (ro) { ro[r * M] = racc[r].x; ro[r * M + 1] = racc[r].y; ro[r * M + 2] = racc[r].z; ro[r * M + 3] = racc[r].w; }
           }
         }
@@ -1348,8 +1349,12 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
   const int WPCi = std::max(1, (INIT_NT / 32) / ncg);
   float* M0 = hM ? hist->M_prev : out->M;                      // memory entering step 0
   const long long sM0 = hM ? (long long)N * M : out->stride_M;
+  // Without a history the initial memory is not copied at all: step 0 reads it where it is (one shared copy when
+  // zero_state broadcasts it, stride 0) and writes the working memory; only its column norms are derived here.
+  const bool lazy_M0 = !hM;
   if (!cont) {
-    init_mem_kernel<<<(unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(in->M, in->stride_M, M0, sM0, cn, N, M, M4, MC, WPCi);
+    init_mem_kernel<<<(unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(in->M, in->stride_M, lazy_M0 ? const_cast<float*>(in->M) : M0,
+                                                                    lazy_M0 ? in->stride_M : sM0, cn, N, M, M4, MC, WPCi);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_mem_kernel");
   }
@@ -1497,8 +1502,8 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       if (prof) cudaEventRecord(g_sev[2 + 4 * t + 2], stream);
       // ---- fused addressing + memory update ----
       ma.t = (int)t; ma.mc = mc_t;
-      ma.Min = hM ? hist->M_prev + (size_t)t * B * N * M : out->M;
-      ma.sMin = hM ? (long long)N * M : out->stride_M;
+      ma.Min = hM ? hist->M_prev + (size_t)t * B * N * M : ((t == 0 && !cont) ? in->M : out->M);
+      ma.sMin = hM ? (long long)N * M : ((t == 0 && !cont) ? in->stride_M : out->stride_M);
       ma.Mout = (hM && !last) ? hist->M_prev + (size_t)(t + 1) * B * N * M : out->M;
       ma.sMout = (hM && !last) ? (long long)N * M : out->stride_M;
       if (hW) {
