@@ -1187,18 +1187,19 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
   if constexpr ((R + W) * CPL > 20) {
     return cudaErrorInvalidValue;
   } else {
-    static int configured = 0;
-    if (configured < smem) {
+    static int configured = 0, occ = 1;      // per instantiation: co-resident CTAs per SM at the configured size
+    if (configured != smem) {
       cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
       configured = smem;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_tma_kernel<R, W, CPL, FULLM>, TMA_NT, smem);
-      if (g_mem_occ < 1) g_mem_occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mem_step_tma_kernel<R, W, CPL, FULLM>, TMA_NT, smem);
+      if (occ < 1) occ = 1;
     }
+    g_mem_occ = occ;
     int nsm = B200_SMS;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = g_mem_occ;
+    int per_sm = occ;
     if (const char* ev = getenv("NTM_B200_MEM_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(ev)));
     const long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
     mem_step_tma_kernel<R, W, CPL, FULLM><<<(unsigned)grid, TMA_NT, smem, stream>>>(a);
