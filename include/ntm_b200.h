@@ -236,7 +236,7 @@ int32_t ntm_b200_finish(void* workspace, void* stream);
  * synchronised ntm_b200_last_kernel_ms returns their device durations. */
 int32_t ntm_b200_set_profiling(int32_t enable);
 int32_t ntm_b200_last_kernel_ms(float* xproj_ms, float* seq_kernel_ms);
-/* Streaming mode (large batches; see DESIGN.md s4.4): with profiling enabled, device time of the last
+/* Streaming mode (large batches; see DESIGN.md s4.3): with profiling enabled, device time of the last
  * call summed over its timesteps, out4 = {controller GEMM + LSTM gates, head-parameter GEMM, fused
  * addressing/memory kernel, state initialisation} in ms; *steps = number of timesteps (0 when the last
  * call on this thread did not run in streaming mode). */

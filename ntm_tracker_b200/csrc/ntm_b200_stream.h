@@ -4,7 +4,7 @@
 // caps the sequences in flight at ~74 (C2 shapes) however large the batch is.  For batches far beyond
 // that the same step is run over ALL sequences of the shard in lockstep: the dense projections become
 // large tensor-core GEMMs and the memory is streamed from HBM by one fused addressing kernel per
-// timestep (one read + one write of M per sequence-step; the second read hits L2).  See DESIGN.md s4.4.
+// timestep (one read + one write of M per sequence-step; the second read hits L2).  See DESIGN.md s4.3.
 #pragma once
 #include <cuda_runtime.h>
 
