@@ -109,6 +109,13 @@ const char* ntm_b200_last_cuda_error(void);
 int32_t ntm_b200_query(const ntm_b200_shape* shape, int64_t batch, int64_t steps,
                        ntm_b200_plan* plan_out);
 
+/* Which execution mode ntm_b200_forward_seq will pick for `batch` sequences of this shape:
+ * *mode_out = 0: the persistent kernel with the memories resident in shared memory (batches of up to a few
+ * waves of resident sequences), 1: the streaming kernels (larger batches; memories streamed from HBM once per
+ * step).  Pure host arithmetic like ntm_b200_query; honours NTM_B200_MODE / NTM_B200_STREAM_MIN_BATCH.  Calls that
+ * request debug taps always run resident. */
+int32_t ntm_b200_query_mode(const ntm_b200_shape* shape, int64_t batch, int32_t* mode_out);
+
 /* One-time repacking of the variables into the kernel's layout (the
  * [C, P+O] concatenation of the two _linear projections of ntm_cell.py:124,220).
  * `packed` is a device buffer of plan.packed_bytes.  Must be re-run when the

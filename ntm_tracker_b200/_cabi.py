@@ -54,6 +54,7 @@ SYMBOLS = {
     "ntm_b200_status_string": (C.c_char_p, [C.c_int32]),
     "ntm_b200_last_cuda_error": (C.c_char_p, []),
     "ntm_b200_query": (C.c_int32, [C.POINTER(Shape), C.c_int64, C.c_int64, C.POINTER(Plan)]),
+    "ntm_b200_query_mode": (C.c_int32, [C.POINTER(Shape), C.c_int64, C.POINTER(C.c_int32)]),
     "ntm_b200_pack_weights": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p,
                                           C.c_int64, C.c_void_p]),
     "ntm_b200_forward_seq": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p,

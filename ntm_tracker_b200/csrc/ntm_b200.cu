@@ -412,6 +412,17 @@ int32_t ntm_b200_query(const ntm_b200_shape* shape, int64_t batch, int64_t steps
   return NTM_B200_OK;
 }
 
+int32_t ntm_b200_query_mode(const ntm_b200_shape* shape, int64_t batch, int32_t* mode_out) {
+  if (!shape || !mode_out) return NTM_B200_ERR_NULL_POINTER;
+  if (batch < 1) return NTM_B200_ERR_BAD_SHAPE;
+  DeviceInfo di = device_info();
+  HostPlan hp{};
+  int st = make_host_plan(shape, di.nsm, di.smem_optin, &hp);
+  if (st) return st;
+  *mode_out = choose_mode(shape, hp, batch, false, di.nsm);
+  return NTM_B200_OK;
+}
+
 int32_t ntm_b200_pack_weights(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
                               void* packed, int64_t packed_bytes, void* stream) {
   if (!shape || !weights || !packed) return NTM_B200_ERR_NULL_POINTER;

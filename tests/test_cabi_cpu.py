@@ -177,3 +177,31 @@ def test_stream_profiling_hooks_answer_without_a_call(lib):
     """The streaming-mode measurement hooks are safe to call when no streaming call ran on this thread."""
     assert _cabi.last_stream_ms()["steps"] == 0
     assert _cabi.stream_phase_ns()["ctas"] == 0
+
+
+def test_execution_mode_choice(lib, monkeypatch):
+    """The planner's choice between the persistent resident kernel and the streaming kernels (host arithmetic):
+    small batches stay resident, batches of many waves stream, shapes the streaming kernels do not cover
+    (mem_dim not a multiple of 4) stay resident whatever the batch, and the environment switch wins."""
+    monkeypatch.delenv("NTM_B200_MODE", raising=False)
+    monkeypatch.delenv("NTM_B200_STREAM_MIN_BATCH", raising=False)
+
+    def mode(shp, B):
+        m = C.c_int32(-1)
+        assert lib.ntm_b200_query_mode(C.byref(shp), B, C.byref(m)) == 0
+        return m.value
+
+    assert mode(shape(), 64) == 0            # BASELINE config 2: one wave of 74 resident sequences
+    assert mode(shape(), 222) == 0           # three waves
+    assert mode(shape(), 256) == 1           # BASELINE config 5 (per GPU)
+    assert mode(shape(), 4096) == 1          # BASELINE config 3
+    assert mode(shape(mem_size=1024, mem_dim=256), 512) == 1     # BASELINE config 4
+    assert mode(shape(mem_dim=510), 4096) == 0                   # not covered by the streaming kernels
+    monkeypatch.setenv("NTM_B200_MODE", "resident")
+    assert mode(shape(), 4096) == 0
+    monkeypatch.setenv("NTM_B200_MODE", "stream")
+    assert mode(shape(), 8) == 1
+    monkeypatch.delenv("NTM_B200_MODE")
+    monkeypatch.setenv("NTM_B200_STREAM_MIN_BATCH", "1000")
+    assert mode(shape(), 512) == 0 and mode(shape(), 1001) == 1
+    assert lib.ntm_b200_query_mode(C.byref(shape()), 0, C.byref(C.c_int32())) == 1
