@@ -531,7 +531,14 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   float* sRed = sPart + NWARP * H;
   const int stage_floats = RPS * M;
   const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
-  constexpr bool hint = true;                  // (the no-hint variant measured the same; compiled out to save issue slots)
+  // L2 eviction hints (measured on the final kernel, C3, same build otherwise): none 494 us per launch and 1.75 GB
+  // of DRAM reads; evict-first on pass-2 loads / stores / parameters only 431 us, 1.31 GB; plus evict-last on the
+  // pass-1 loads (below) 422 us, 1.43 GB.  -DNTM_NO_L2_HINTS rebuilds the first variant.
+#ifdef NTM_NO_L2_HINTS
+  constexpr bool hint = false;
+#else
+  constexpr bool hint = true;
+#endif
   // pass 1 brings the rows in and wants them to survive in L2 until pass 2 re-reads them; after that
   // re-read, and for the rewritten rows, the next use is a whole timestep (the other sequences) away
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
