@@ -403,7 +403,8 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "ntm_seq_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+        "kernel": ("stream_forward (mem_step_tma_kernel + gemm_ws_kernel + lstm_stream_kernel, whole forward)"
+                   if info.get("streaming") else "ntm_seq_kernel"), "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_seq_step": abytes, "kernel_ms": seq_avg_ms,
         "kernel_share_of_step": seq_avg_ms / (sum(prof_step_ms) / len(prof_step_ms)),
@@ -422,7 +423,7 @@ def main():
         achieved = abytes * B_local / (mem_launch_ms / 1e3) / 1e9
         step_avg = sum(prof_step_ms) / len(prof_step_ms)
         roofline = {
-            "kernel": "mem_step_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "kernel": "mem_step_tma_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_seq_step": abytes, "units_per_launch": B_local,
             "kernel_ms": mem_launch_ms, "launches_per_step": T, "ctas_per_sm": info.get("ctas_per_sm"),
