@@ -196,7 +196,9 @@ int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* shape, int64_t batch
  * serialize: conv features [B, L, F, Cch] + first-frame target map [B, F] -> tracker inputs
  * [B, L*(F+1), Cch+2] with a delimiter row per frame (last row of the frame as in training,
  * direct_offset_output.py:439-500; first row when delimiter_first != 0 as in the serve path,
- * test_tracker.py:400-404), channel Cch = delimiter bit, channel Cch+1 = target (first F steps).
+ * test_tracker.py:385-404), channel Cch = delimiter bit, channel Cch+1 = target[b, f] on the F feature
+ * rows of the FIRST frame only (training layout: steps 0..F-1; serve layout: steps 1..F), 0 on every
+ * delimiter row and on all later frames.
  * gather: logits [B, L*(F+1), O] -> tanh(logits at each frame's delimiter row, first frame
  * dropped) [B, L-1, O]  (direct_offset_output.py:581-593). */
 int32_t ntm_b200_serialize_tracker_inputs(const float* features, const float* target, float* inputs,

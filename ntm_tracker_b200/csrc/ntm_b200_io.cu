@@ -2,10 +2,12 @@
 //
 //  * serialise:  conv features [B, L, F, Cch] + first-frame target map [B, F]
 //                -> tracker inputs [B, L*(F+1), Cch+2]      (direct_offset_output.py:439-500)
-//       row (l, f<F) = [features[b,l,f,:], 0, target]; row (l, F) = frame delimiter = [0...0, 1, target];
-//       the target channel carries target[b, t] on the first F steps of the sequence and 0 afterwards.
+//       row (l, f<F) = [features[b,l,f,:], 0, target]; row (l, F) = frame delimiter = [0...0, 1, 0];
+//       the target channel carries target[b, f] on the F FEATURE rows of the first frame and 0 everywhere
+//       else (training layout: those are steps 0..F-1, direct_offset_output.py:490-494).
 //       `delimiter_first` puts the delimiter row at the START of every frame instead, which is the
-//       serve path's layout (test_tracker.py:400-404).
+//       serve path's layout (test_tracker.py:385-404: rows [feat_f, 0, gt_f] with the delimiter
+//       [0...0, 1, 0] prepended) -- there feature f of the first frame is step f + 1.
 //  * gather:     logits [B, L*(F+1), O] -> tanh(logits at every frame's delimiter row, first frame
 //                dropped) [B, L-1, O]                        (direct_offset_output.py:581-593)
 // Pure HBM-bound copies: one pass, coalesced (float2 where the row strides allow).
@@ -34,7 +36,7 @@ __global__ void serialize_kernel(const float* __restrict__ feat, const float* __
     float v;
     if (col < Cch) v = is_delim ? 0.0f : __ldg(feat + (((b * L + l) * F + f) * (long long)Cch + col));
     else if (col == Cch) v = is_delim ? 1.0f : 0.0f;
-    else v = (t < F) ? __ldg(target + b * F + t) : 0.0f;
+    else v = (l == 0 && !is_delim) ? __ldg(target + b * F + f) : 0.0f;
     out[i] = v;
   }
 }

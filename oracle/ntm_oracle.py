@@ -362,18 +362,20 @@ def tracker_inputs(B: int, T: int, seed: int, scale: float = 1.0,
 
 
 def serialize_tracker_inputs(features, target, delimiter_first=False):
-    """direct_offset_output.py:439-500 (delimiter row last) / test_tracker.py:392-404 (first).
-    features [B,L,F,C], target [B,F] -> [B, L*(F+1), C+2]."""
+    """direct_offset_output.py:439-500 (training layout, delimiter row last in every frame) /
+    test_tracker.py:385-404 (serve layout, delimiter row first).
+    features [B,L,F,C], target [B,F] -> [B, L*(F+1), C+2].  The target channel sits on the F feature rows
+    of the FIRST frame (training: steps 0..F-1, :490-494; serve: rows [feat_f, 0, gt_f] built before the
+    delimiter [0..0,1,0] is prepended, so steps 1..F) and is zero everywhere else."""
     features = np.asarray(features)
     B, L, F, Cc = features.shape
-    padded = np.concatenate([features, np.zeros((B, L, F, 1), features.dtype)], 3)       # :463-464
-    delim = np.zeros((B, L, 1, Cc + 1), features.dtype)
+    tgt = np.zeros((B, L, F, 1), features.dtype)
+    tgt[:, 0, :, 0] = np.asarray(target, features.dtype)                                  # gts[:, 0, :], :456
+    padded = np.concatenate([features, np.zeros((B, L, F, 1), features.dtype), tgt], 3)   # :463-464, :496-498
+    delim = np.zeros((B, L, 1, Cc + 2), features.dtype)
     delim[..., Cc] = 1.0                                                                  # :467-475
-    frames = np.concatenate([delim, padded] if delimiter_first else [padded, delim], 2)  # :478-479
-    frames = frames.reshape(B, L * (F + 1), Cc + 1)                                       # :481-486
-    tgt = np.concatenate([np.asarray(target, features.dtype),
-                          np.zeros((B, (L - 1) * (F + 1) + 1), features.dtype)], 1)       # :490-494
-    return np.concatenate([frames, tgt[..., None]], -1)                                   # :496-498
+    frames = np.concatenate([delim, padded] if delimiter_first else [padded, delim], 2)  # :478-479 / test_tracker.py:404
+    return frames.reshape(B, L * (F + 1), Cc + 2)                                         # :481-486
 
 
 def gather_offsets(output_logits, num_features):

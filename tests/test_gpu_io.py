@@ -23,7 +23,32 @@ def test_serialize_matches_reference_layout(B, L, F, C, first):
     # structure: one delimiter bit per frame, target only within the first F steps
     x = got.cpu().numpy()
     assert x[:, :, C].sum() == B * L
-    assert np.abs(x[:, F:, C + 1]).sum() == 0
+    first_frame = x[:, :F + 1, C + 1]
+    assert np.abs(x[:, F + 1:, C + 1]).sum() == 0                       # target only inside the first frame ...
+    assert np.array_equal(first_frame[:, 1:] if first else first_frame[:, :F], tgt)   # ... on its feature rows
+
+
+def test_serialize_matches_reference_golden_layouts(golden_dir):
+    """Against the rows the reference's OWN statements produce (oracle/make_golden_layout.py): serve
+    layout test_tracker.py:380-404 (per frame and all frames at once), training layout
+    direct_offset_output.py:439-500, gather :581-593."""
+    import os
+    from ntm_tracker_b200.serialize import gather_offsets, tracker_inputs
+    z = np.load(os.path.join(golden_dir, "layout_serve.npz"))
+    feats, gt, rows = z["features"], z["gt"], z["rows"]
+    nfr, F, Cc = feats.shape
+    for i in range(nfr):
+        tgt = gt[None] if i == 0 else np.zeros((1, F), np.float32)
+        got = tracker_inputs(torch.from_numpy(feats[i][None, None]).cuda(), torch.from_numpy(tgt).cuda(),
+                             delimiter_first=True)
+        assert np.array_equal(got.cpu().numpy()[0], rows[i]), i
+    got = tracker_inputs(torch.from_numpy(feats[None]).cuda(), torch.from_numpy(gt[None]).cuda(), delimiter_first=True)
+    assert np.array_equal(got.cpu().numpy()[0], rows.reshape(nfr * (F + 1), Cc + 2))
+    z = np.load(os.path.join(golden_dir, "layout_train.npz"))
+    got = tracker_inputs(torch.from_numpy(z["features"]).cuda(), torch.from_numpy(z["target"]).cuda())
+    assert np.array_equal(got.cpu().numpy(), z["inputs"])
+    off = gather_offsets(torch.from_numpy(z["logits"]).cuda(), z["features"].shape[2]).cpu().numpy()
+    assert np.abs(off - z["offsets"]).max() <= 1e-6
 
 
 @pytest.mark.parametrize("B,L,F,Od", [(4, 5, 64, 2), (2, 2, 3, 5)])

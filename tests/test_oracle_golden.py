@@ -132,5 +132,33 @@ def test_degenerate_inputs_no_nan():
 def test_all_golden_files_present(golden_dir):
     have = {os.path.basename(p) for p in glob.glob(os.path.join(golden_dir, "*.npz"))}
     need = {c + ".npz" for c in CASES} | {"kat_similarity.npz", "kat_circular_conv_s3.npz",
-                                          "kat_circular_conv_s5.npz"}
+                                          "kat_circular_conv_s5.npz", "layout_serve.npz", "layout_train.npz"}
     assert need <= have
+
+
+def test_serve_layout_matches_reference_rows(golden_dir):
+    """test_tracker.py:380-404 executed by oracle/make_golden_layout.py: delimiter row [0..0,1,0] FIRST,
+    then rows [feat_f, 0, gt_f] on the first frame and [feat_f, 0, 0] afterwards -- feature f of the
+    first frame is step f + 1 and the delimiter's target bit is 0."""
+    z = np.load(os.path.join(golden_dir, "layout_serve.npz"))
+    feats, gt, rows = z["features"], z["gt"], z["rows"]
+    nfr, F, Cc = feats.shape
+    # frame by frame, the way ResidentTracker.track feeds them (target zeros after the first frame)
+    for i in range(nfr):
+        tgt = gt[None] if i == 0 else np.zeros((1, F), np.float32)
+        got = O.serialize_tracker_inputs(feats[i][None, None], tgt, delimiter_first=True)
+        assert np.array_equal(got[0], rows[i]), i
+    # all frames of the sequence in one call
+    got = O.serialize_tracker_inputs(feats[None], gt[None], delimiter_first=True)
+    assert np.array_equal(got[0], rows.reshape(nfr * (F + 1), Cc + 2))
+    assert rows[0, 0, Cc] == 1.0 and rows[0, 0, Cc + 1] == 0.0
+    assert np.array_equal(rows[0, 1:, Cc + 1], gt) and np.abs(rows[1:, :, Cc + 1]).sum() == 0
+
+
+def test_training_layout_and_gather_match_reference_statements(golden_dir):
+    """direct_offset_output.py:439-500 and :581-593 executed under the TF1 shim."""
+    z = np.load(os.path.join(golden_dir, "layout_train.npz"))
+    got = O.serialize_tracker_inputs(z["features"], z["target"], delimiter_first=False)
+    assert np.array_equal(got, z["inputs"])
+    F = z["features"].shape[2]
+    np.testing.assert_allclose(O.gather_offsets(z["logits"], F), z["offsets"], rtol=0, atol=1e-6)
