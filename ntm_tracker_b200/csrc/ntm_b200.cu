@@ -48,6 +48,25 @@ namespace {
 std::atomic<long long> g_launches{0};
 }
 void ntm_b200::count_launch() { g_launches++; }
+std::mutex& ntm_b200::config_mutex() {
+  static std::mutex m;
+  return m;
+}
+ntm_b200::EnvSwitches ntm_b200::read_env() {
+  EnvSwitches e{};
+  const char* m = getenv("NTM_B200_MODE");
+  e.mode = (m == nullptr) ? -1 : (m[0] == 'r' ? 0 : (m[0] == 's' ? 1 : -1));
+  const char* t = getenv("NTM_B200_STREAM_MIN_BATCH");
+  e.stream_min_batch = t != nullptr ? atoll(t) : -1;
+  e.disable_tc = getenv("NTM_B200_DISABLE_TC") != nullptr;
+  e.dual_team = getenv("NTM_B200_DUAL_TEAM") != nullptr;
+  e.no_coop = getenv("NTM_B200_NO_COOP") != nullptr;
+  e.no_tma_ring = getenv("NTM_B200_NO_TMA_RING") != nullptr;
+  e.old_gemm = getenv("NTM_B200_OLD_GEMM") != nullptr;
+  const char* c = getenv("NTM_B200_MEM_CTAS_PER_SM");
+  e.mem_ctas_per_sm = c != nullptr ? atoi(c) : 0;
+  return e;
+}
 
 namespace {
 thread_local char g_cuda_err[256] = "";
@@ -170,7 +189,7 @@ bool layout_for(const ntm_b200_shape* s, int CS, int nwarp, int budget, HostPlan
   return true;
 }
 
-int make_host_plan(const ntm_b200_shape* s, int nsm, int smem_optin, HostPlan* hp) {
+int make_host_plan(const ntm_b200_shape* s, int nsm, int smem_optin, const EnvSwitches& env, HostPlan* hp) {
   int st = validate_shape(s);
   if (st) return st;
   // Experimental (NTM_B200_DUAL_TEAM=1, tensor path only): 256-thread CTAs, two per SM, as two
@@ -180,7 +199,7 @@ int make_host_plan(const ntm_b200_shape* s, int nsm, int smem_optin, HostPlan* h
   const int half_budget = std::min(smem_optin, B200_SMEM_SM / 2 - 1024 - 2048);   // slack for allocation granularity
   bool ok = false;
   // (tensor path only: with the SIMT GEMMs the two-team build is known to time out at 35 sequences per team)
-  if (getenv("NTM_B200_DUAL_TEAM") != nullptr && getenv("NTM_B200_DISABLE_TC") == nullptr) {
+  if (env.dual_team && !env.disable_tc) {
     for (int CS = 1; CS <= 8 && !ok; CS *= 2) {
       if (layout_for(s, CS, 8, half_budget, hp)) {
         ok = true;
@@ -256,10 +275,10 @@ bool plan_gemm_tc(int K, int NC, int NCs, int ldw, int lda, int G, int ncta, int
 // All GEMM plans of one team.  The tensor path is used when every GEMM's weight tile fits the
 // CTA's TMEM columns next to the accumulator (else the SIMT path, e.g. for small grids).
 void choose_plans(const ntm_b200_shape* s, const HostPlan& hp, int G, int ncta, bool allow_tc,
-                  GemmPlan* gA, GemmPlan* gC, int* use_tc) {
+                  GemmPlan* gA, GemmPlan* gC, int* use_tc) {   // allow_tc already folds in NTM_B200_DISABLE_TC
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int scr_bytes = 4 * hp.scr_floats;
-  bool tc = allow_tc && getenv("NTM_B200_DISABLE_TC") == nullptr;
+  bool tc = allow_tc;
   if (tc) {
     int col = round_up(round_up(std::max(G, 1), 16), 32);     // accumulator columns first
     for (int l = 0; l < L && tc; ++l) {
@@ -308,7 +327,7 @@ void layout_workspace(const ntm_b200_shape* s, const HostPlan& hp, long long B, 
     for (int variant = 0; variant < 2; ++variant) {
       GemmPlan gA[MAXL], gC;
       int use_tc = 0;
-      choose_plans(s, hp, G, ncta, variant == 1, gA, &gC, &use_tc);
+      choose_plans(s, hp, G, ncta, variant == 1, gA, &gC, &use_tc);   // both paths: sized for either
       for (int l = 0; l < L; ++l) pa = std::max(pa, (long long)gA[l].KS * gA[l].Gpad * gA[l].NCs);
       pc = std::max(pc, (long long)gC.KS * gC.Gpad * gC.NCs);
     }
@@ -346,16 +365,13 @@ int check_state(const ntm_b200_state* st) {
 
 // Execution mode for a call: 0 = persistent shared-memory-resident kernel, 1 = streaming (lockstep over
 // the whole shard, memory streamed from HBM).  NTM_B200_MODE=resident|stream overrides the choice.
-int choose_mode(const ntm_b200_shape* s, const HostPlan& hp, long long B, bool debug_taps, int nsm) {
+int choose_mode(const ntm_b200_shape* s, const HostPlan& hp, long long B, bool debug_taps, int nsm, const EnvSwitches& env) {
   if (debug_taps || !stream_supported(s, nsm)) return 0;
-  const char* m = getenv("NTM_B200_MODE");
-  if (m != nullptr && m[0] == 'r') return 0;
-  if (m != nullptr && m[0] == 's') return 1;
+  if (env.mode >= 0) return env.mode;
   // resident: ceil(B / G) waves of ~30 us steps; streaming pays ~4 launches + GEMM weight loads per step
   // but its step time grows only with the HBM traffic.  Measured crossover (profiles/): a few waves.
   long long thr = 3ll * hp.Gteam_max * hp.max_teams;
-  const char* t = getenv("NTM_B200_STREAM_MIN_BATCH");
-  if (t != nullptr) thr = atoll(t);
+  if (env.stream_min_batch >= 0) thr = env.stream_min_batch;
   return B > thr ? 1 : 0;
 }
 
@@ -391,8 +407,9 @@ int32_t ntm_b200_query(const ntm_b200_shape* shape, int64_t batch, int64_t steps
   if (!shape || !plan_out) return NTM_B200_ERR_NULL_POINTER;
   if (batch < 1 || steps < 1) return NTM_B200_ERR_BAD_SHAPE;
   DeviceInfo di = device_info();
+  const EnvSwitches env = read_env();
   HostPlan hp{};
-  int st = make_host_plan(shape, di.nsm, di.smem_optin, &hp);
+  int st = make_host_plan(shape, di.nsm, di.smem_optin, env, &hp);
   if (st) return st;
   Workspace ws{};
   layout_workspace(shape, hp, batch, steps, &ws);
@@ -416,10 +433,11 @@ int32_t ntm_b200_query_mode(const ntm_b200_shape* shape, int64_t batch, int32_t*
   if (!shape || !mode_out) return NTM_B200_ERR_NULL_POINTER;
   if (batch < 1) return NTM_B200_ERR_BAD_SHAPE;
   DeviceInfo di = device_info();
+  const EnvSwitches env = read_env();
   HostPlan hp{};
-  int st = make_host_plan(shape, di.nsm, di.smem_optin, &hp);
+  int st = make_host_plan(shape, di.nsm, di.smem_optin, env, &hp);
   if (st) return st;
-  *mode_out = choose_mode(shape, hp, batch, false, di.nsm);
+  *mode_out = choose_mode(shape, hp, batch, false, di.nsm, env);
   return NTM_B200_OK;
 }
 
@@ -428,7 +446,7 @@ int32_t ntm_b200_pack_weights(const ntm_b200_shape* shape, const ntm_b200_weight
   if (!shape || !weights || !packed) return NTM_B200_ERR_NULL_POINTER;
   DeviceInfo di = device_info();
   HostPlan hp{};
-  int st = make_host_plan(shape, di.nsm, di.smem_optin, &hp);
+  int st = make_host_plan(shape, di.nsm, di.smem_optin, read_env(), &hp);
   if (st) return st;
   if (!di.ok) return NTM_B200_ERR_NO_DEVICE;
   if (packed_bytes < hp.packed_bytes) return NTM_B200_ERR_WORKSPACE;
@@ -457,8 +475,12 @@ int32_t ntm_b200_forward_seq(const ntm_b200_shape* shape, const ntm_b200_weights
 }
 
 // What the last streaming call of this thread left valid in its workspace (for ntm_b200_forward_seq_continue).
-struct StreamResume { void* workspace; const float* M; long long batch; ntm_b200_shape shape; const void* packed; };
-static thread_local StreamResume g_resume = {nullptr, nullptr, 0, {}, nullptr};
+struct StreamResume { void* workspace; const float* M; long long batch; ntm_b200_shape shape; const void* packed; void* stream; };
+static thread_local StreamResume g_resume = {nullptr, nullptr, 0, {}, nullptr, nullptr};
+static thread_local StreamResume g_resume_prev = {nullptr, nullptr, 0, {}, nullptr, nullptr};
+// Every call invalidates the record first (a resident-mode or debug call on the same workspace overwrites the
+// streaming layout); only a streaming call without history re-arms it.
+static void g_resume_reset() { g_resume_prev = g_resume; g_resume.workspace = nullptr; }
 
 static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
                             const void* packed, int64_t batch, int64_t steps,
@@ -498,10 +520,12 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   if (st) return st;
   if (batch < 1 || steps < 1 || batch > (1 << 24) || steps > (1 << 24)) return NTM_B200_ERR_BAD_SHAPE;
   DeviceInfo di = device_info();
+  const EnvSwitches env = read_env();
   HostPlan hp{};
-  st = make_host_plan(shape, di.nsm, di.smem_optin, &hp);
+  st = make_host_plan(shape, di.nsm, di.smem_optin, env, &hp);
   if (st) return st;
   if (!di.ok) return NTM_B200_ERR_NO_DEVICE;
+  g_resume_reset();
   const int L = shape->controller_num_layers, C = shape->controller_hidden_size;
   for (int l = 0; l < L; ++l)
     if (!weights->lstm_w[l] || !weights->lstm_b[l]) return NTM_B200_ERR_NULL_POINTER;
@@ -509,7 +533,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   layout_workspace(shape, hp, batch, steps, &ws);
   StreamWorkspace sws{};
   stream_layout(shape, batch, steps, &sws);
-  const int mode = choose_mode(shape, hp, batch, debug_taps != nullptr, di.nsm);
+  const int mode = choose_mode(shape, hp, batch, debug_taps != nullptr, di.nsm, env);
   if (workspace_bytes < (mode ? sws.total + 1024 : ws.total)) return NTM_B200_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char* wsb = static_cast<char*>(workspace);
@@ -545,7 +569,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   // tensor-core kernel (tcgen05, weight tile resident in TMEM + SMEM); fp32 SIMT kernel for shapes it
   // does not cover or when NTM_B200_DISABLE_TC is set
   st = -1;
-  if (getenv("NTM_B200_DISABLE_TC") == nullptr)
+  if (!env.disable_tc)
     st = ntm_b200::launch_xproj_tc(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
                                    (long long)batch * steps, shape->input_dim, 4 * C, di.nsm, stream);
   g_last_info[12] = (st == 0) ? 1 : 0;
@@ -562,14 +586,14 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
     const float* wCp = static_cast<const float*>(packed);
     // continuation: same workspace, batch, shape and packed weights as the last streaming call, and the state
     // it left (updated in place) -- otherwise this is an ordinary call
-    const bool cont = want_cont && g_resume.workspace == workspace && g_resume.batch == batch &&
-                      g_resume.M == state_in->M && state_in->M == state_out->M && g_resume.packed == packed &&
-                      memcmp(&g_resume.shape, shape, sizeof(*shape)) == 0;
-    g_resume.workspace = nullptr;
+    const StreamResume& rs = g_resume_prev;   // what the call before this one left (g_resume itself is already reset)
+    const bool cont = want_cont && rs.workspace == workspace && rs.batch == batch && rs.stream == stream_v &&
+                      rs.M == state_in->M && state_in->M == state_out->M && rs.packed == packed &&
+                      memcmp(&rs.shape, shape, sizeof(*shape)) == 0;
     st = stream_forward(shape, weights, wCp, wCp + (size_t)C * hp.PO4, batch, steps, xw, state_in, state_out,
-                        logits, outputs, history, swsb, sws, di.nsm, stream, prof, cont);
+                        logits, outputs, history, swsb, sws, di.nsm, stream, prof, cont, env);
     if (st) return st;
-    if (history == nullptr) g_resume = StreamResume{workspace, state_out->M, (long long)batch, *shape, packed};
+    if (history == nullptr) g_resume = StreamResume{workspace, state_out->M, (long long)batch, *shape, packed, stream_v};
     g_last_info[14] = cont ? 1 : 0;
     if (prof) {
       cudaEventRecord(g_ev[2], stream);
@@ -595,7 +619,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
     p.wA[l] = weights->lstm_w[l] + (l == 0 ? (size_t)shape->input_dim * 4 * C : 0);
     p.bA[l] = weights->lstm_b[l];
   }
-  choose_plans(shape, hp, G, ncta, true, p.gA, &p.gC, &p.use_tc);
+  choose_plans(shape, hp, G, ncta, !env.disable_tc, p.gA, &p.gC, &p.use_tc);
   g_last_info[0] = p.use_tc; g_last_info[1] = G * nteams; g_last_info[2] = ncta * nteams; g_last_info[3] = hp.CS;
   g_last_info[4] = p.gA[0].KS; g_last_info[5] = p.gA[0].KW; g_last_info[6] = p.gC.KS; g_last_info[7] = p.gC.KW;
   g_last_info[8] = nteams; g_last_info[9] = kv.threads; g_last_info[10] = kv.ctas_per_sm; g_last_info[11] = smem_bytes;
@@ -630,14 +654,11 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   // cluster + cooperative (co-residency enforced by the driver).  NTM_B200_NO_COOP=1 drops the
   // cooperative attribute (the grid is sized from the occupancy query, so the CTAs are still
   // co-resident); needed under Nsight Compute, whose kernel replay rejects cooperative+cluster launches.
-  const bool coop = kv.cooperative_ok && getenv("NTM_B200_NO_COOP") == nullptr;
+  // A rejected cooperative launch is an ERROR (the kernel contains a device-wide barrier; without the
+  // driver's co-residency guarantee a concurrent kernel could starve it) -- there is no silent relaunch.  The
+  // two-team experiment build (NTM_B200_DUAL_TEAM) cannot be launched cooperatively and stays opt-in.
+  const bool coop = kv.cooperative_ok && !env.no_coop;
   e = kv.launch(R, W, p, ncta * nteams, hp.CS, smem_bytes, coop, stream);
-  if (e != cudaSuccess && coop) {
-    // some driver/toolkit combinations reject cooperative+cluster; the grid is
-    // sized from the occupancy query, so co-residency still holds.
-    cudaGetLastError();
-    e = kv.launch(R, W, p, ncta * nteams, hp.CS, smem_bytes, false, stream);
-  }
   g_launches++;
   if (e != cudaSuccess) return set_cuda_error(e, "cudaLaunchKernelEx(ntm_seq_kernel)");
   if (prof) {

@@ -23,6 +23,7 @@
 
 #include <cstdint>
 
+#include "ntm_b200_params.h"
 #include "ntm_b200_umma.cuh"
 
 namespace ntm_b200 {
@@ -347,11 +348,15 @@ inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi
   a.ncols = p.ncols; a.ntiles = p.ntiles; a.kslices = p.kslices; a.ngroups = p.ngroups; a.KAtot = p.KAtot; a.KA = p.KA;
   a.nslot = p.nslot; a.wlo_tmem = p.wlo_tmem;
   const int smem = smem_bytes(p);
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
+  static int configured[MAX_DEVICES] = {0};     // cudaFuncSetAttribute is per device
+  {
+    std::lock_guard<std::mutex> lk(config_mutex());
+    const int dev = current_device_slot();
+    if (configured[dev] < smem) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      configured[dev] = smem;
+    }
   }
   gemm_ws_kernel<<<p.ntiles * p.kslices * p.ngroups, THREADS, smem, stream>>>(a);
   return cudaGetLastError();

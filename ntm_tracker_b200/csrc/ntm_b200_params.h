@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "ntm_b200.h"
 
 namespace ntm_b200 {
@@ -77,6 +79,30 @@ struct KernelVariant {
   cudaError_t (*launch)(int R, int W, const KParams& p, int grid_ctas, int cluster_size, int smem_bytes,
                         bool cooperative, cudaStream_t stream);
 };
+// cudaFuncSetAttribute / occupancy results are PER DEVICE: launchers remember what they configured per
+// (kernel instantiation, device) in a function-local `static int cfg[MAX_DEVICES]`, under this mutex.
+constexpr int MAX_DEVICES = 64;
+std::mutex& config_mutex();
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+  return (d < 0 || d >= MAX_DEVICES) ? 0 : d;
+}
+
+// Environment switches (experiments / debugging), read ONCE per C-ABI call by read_env() and handed
+// down, never inside the per-timestep loops.
+struct EnvSwitches {
+  int mode;                  // NTM_B200_MODE: -1 automatic, 0 resident, 1 stream
+  long long stream_min_batch;// NTM_B200_STREAM_MIN_BATCH (-1 = default threshold)
+  bool disable_tc;           // NTM_B200_DISABLE_TC
+  bool dual_team;            // NTM_B200_DUAL_TEAM
+  bool no_coop;              // NTM_B200_NO_COOP (needed under Nsight Compute kernel replay)
+  bool no_tma_ring;          // NTM_B200_NO_TMA_RING
+  bool old_gemm;             // NTM_B200_OLD_GEMM
+  int mem_ctas_per_sm;       // NTM_B200_MEM_CTAS_PER_SM (0 = occupancy)
+};
+EnvSwitches read_env();
+
 void count_launch();   // bumps the library-wide kernel-launch counter (ntm_b200_launch_count)
 namespace k512 { const KernelVariant& variant(); }
 namespace k256 { const KernelVariant& variant(); }

@@ -978,6 +978,16 @@ __global__ void NTM_KERNEL_BOUNDS ntm_seq_kernel(const KParams p) {
     }
 
     // ---- epilogue: final state (ntm_cell.py:223-228) ----
+    // A grid barrier that timed out (error flag) means the steps above ran on unsynchronised data: the
+    // barriers pass at once from then on, so the kernel still ends in bounded time, and the results of
+    // this call are POISONED (NaN logits / outputs) so that no caller can mistake them for an answer.
+    if (active && crank == 0 && *reinterpret_cast<volatile int*>(p.err) != 0) {
+      const float qnan = __int_as_float(0x7fc00000);
+      for (int i = tid; i < p.T * p.O; i += NT) {
+        p.logits[(size_t)bglob * p.T * p.O + i] = qnan;
+        if (p.outputs != nullptr) p.outputs[(size_t)bglob * p.T * p.O + i] = qnan;
+      }
+    }
     if (active) {
       float* dstM = p.dM + (size_t)bglob * p.dsM;
       for (int i = tid; i < nrows * p.M; i += NT) {

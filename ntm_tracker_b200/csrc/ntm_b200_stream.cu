@@ -1151,16 +1151,22 @@ __global__ void lstm_stream_kernel(const LstmArgs a) {
 
 // ------------------------------------------------------------------------------------- host side --
 constexpr int MEM_NT = 256;
-int g_mem_occ = 0;
+thread_local int g_mem_occ = 0;
+thread_local int g_env_mem_ctas_per_sm = 0;   // EnvSwitches::mem_ctas_per_sm of the call in progress
 
 template <int R, int W, int NT, int MINB>
 cudaError_t launch_mem_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(mem_step_kernel<R, W, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_mem_occ, mem_step_kernel<R, W, NT, MINB>, NT, smem);
+  static int configured[MAX_DEVICES] = {0}, occs[MAX_DEVICES] = {0};   // per instantiation AND device
+  {
+    std::lock_guard<std::mutex> lk(config_mutex());
+    const int dev = current_device_slot();
+    if (configured[dev] < smem) {
+      cudaError_t e = cudaFuncSetAttribute(mem_step_kernel<R, W, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      configured[dev] = smem;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs[dev], mem_step_kernel<R, W, NT, MINB>, NT, smem);
+    }
+    g_mem_occ = occs[dev];
   }
   mem_step_kernel<R, W, NT, MINB><<<(unsigned)B, NT, smem, stream>>>(a);
   return cudaGetLastError();
@@ -1194,20 +1200,27 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
   if constexpr ((R + W) * CPL > 20) {
     return cudaErrorInvalidValue;
   } else {
-    static int configured = 0, occ = 1;      // per instantiation: co-resident CTAs per SM at the configured size
-    if (configured != smem) {
-      cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      configured = smem;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mem_step_tma_kernel<R, W, CPL, FULLM>, TMA_NT, smem);
-      if (occ < 1) occ = 1;
+    // per instantiation AND device: configured size, co-resident CTAs per SM at that size, SM count
+    static int configured[MAX_DEVICES] = {0}, occs[MAX_DEVICES] = {0}, sms[MAX_DEVICES] = {0};
+    int occ = 1, nsm = B200_SMS;
+    {
+      std::lock_guard<std::mutex> lk(config_mutex());
+      const int dev = current_device_slot();
+      if (configured[dev] != smem) {
+        cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = smem;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs[dev], mem_step_tma_kernel<R, W, CPL, FULLM>, TMA_NT, smem);
+        if (occs[dev] < 1) occs[dev] = 1;
+        int rdev = 0;
+        sms[dev] = B200_SMS;
+        if (cudaGetDevice(&rdev) == cudaSuccess) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, rdev);
+      }
+      occ = occs[dev]; nsm = sms[dev];
     }
     g_mem_occ = occ;
-    int nsm = B200_SMS;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     int per_sm = occ;
-    if (const char* ev = getenv("NTM_B200_MEM_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(ev)));
+    if (g_env_mem_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, g_env_mem_ctas_per_sm));
     const long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
     mem_step_tma_kernel<R, W, CPL, FULLM><<<(unsigned)grid, TMA_NT, smem, stream>>>(a);
     return cudaGetLastError();
@@ -1328,7 +1341,9 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
 int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const float* wC, const float* bC,
                    long long B, long long T, const float* xw, const ntm_b200_state* in,
                    const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
-                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont) {
+                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont,
+                   const EnvSwitches& env) {
+  g_env_mem_ctas_per_sm = env.mem_ctas_per_sm;
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W, S = 2 * s->shift_range + 1;
   const int N = s->mem_size, M = s->mem_dim, M4 = round_up(M, 4), MC = M4 / 4, Npad = round_up(N, 4);
@@ -1382,7 +1397,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
   // ---- warp-specialised tensor-core GEMMs (single-layer controller, M and C multiples of 8, TMA memory
   //      kernel): operands pre-split into bf16 hi/lo tile records by their producers ----
   const bool use_ws = (L == 1) && (M % 8 == 0) && (C % 8 == 0) && tma_rps(N, M) > 0 && tma_cpl(H, MC) > 0 &&
-                      getenv("NTM_B200_NO_TMA_RING") == nullptr && getenv("NTM_B200_OLD_GEMM") == nullptr;
+                      !env.no_tma_ring && !env.old_gemm;
   gemmws::Plan planA{}, planC{};
   uint8_t* tilesA = reinterpret_cast<uint8_t*>(wsb + ws.off_tilesA);
   uint8_t* tilesC = reinterpret_cast<uint8_t*>(wsb + ws.off_tilesC);
@@ -1426,7 +1441,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     const int smem = 4 * o;
     // TMA-ring kernel (when it covers the shape): its own carve-up replaces the generic one
     int smem_tma = 0;
-    const int cpl = (getenv("NTM_B200_NO_TMA_RING") == nullptr && tma_rps(N, M) > 0) ? tma_cpl(H, MC) : 0;
+    const int cpl = (!env.no_tma_ring && tma_rps(N, M) > 0) ? tma_cpl(H, MC) : 0;
     if (cpl) {
       int o2 = 0;
       auto take2 = [&](int n) { int r = o2; o2 += round_up(n, 4); return r; };

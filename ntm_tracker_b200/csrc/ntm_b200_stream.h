@@ -35,7 +35,8 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
 int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const float* wC, const float* bC,
                    long long B, long long T, const float* xw, const ntm_b200_state* in,
                    const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
-                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont = false);
+                   char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont,
+                   const EnvSwitches& env);
 
 // profiling (after the stream was synchronised): {controller GEMM + LSTM, head-parameter GEMM, memory
 // kernel, init} summed over the T steps, in ms; returns the number of memory-kernel launches (0 = none)

@@ -17,6 +17,7 @@
 
 #include <cstdint>
 
+#include "ntm_b200_params.h"
 #include "ntm_b200_umma.cuh"
 
 namespace ntm_b200 {
@@ -216,13 +217,17 @@ inline int launch_gemm_tc(const float* x, int ldx, const float* w, int ldw, cons
   a.ngroups = (int)(nrb < (long long)(nsm / units) ? nrb : (long long)(nsm / units));
   if (a.ngroups < 1) a.ngroups = 1;
   const int smem = 1024 + a.katoms * 128 * 128 + 2 * 2 * XT_ROWS * 128;
-  static int configured = 0;
-  if (configured < smem) {
-    if (cudaFuncSetAttribute(xproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      cudaGetLastError();
-      return -1;
+  static int configured[MAX_DEVICES] = {0};     // cudaFuncSetAttribute is per device
+  {
+    std::lock_guard<std::mutex> lk(config_mutex());
+    const int dev = current_device_slot();
+    if (configured[dev] < smem) {
+      if (cudaFuncSetAttribute(xproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+      }
+      configured[dev] = smem;
     }
-    configured = smem;
   }
   xproj_tc_kernel<<<units * a.ngroups, XT_THREADS, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -241,9 +241,14 @@ class NTMCell(object):
         `workspace`: caller-provided scratch tensor (else cached per geometry).  `continuation`: this call
         advances the sequences of the previous call on the same workspace; `state` (that call's new_state) is
         updated in place and returned (ntm_b200_forward_seq_continue)."""
-        lib = _cabi.load()
         if not torch.cuda.is_available():
             raise RuntimeError("ntm_tracker_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        # the library launches on the CURRENT device with the stream it is handed: pin both to the cell's device
+        with torch.cuda.device(self.device):
+            return self._run_on_device(inputs, state, steps, history, workspace, continuation)
+
+    def _run_on_device(self, inputs, state, steps, history, workspace, continuation):
+        lib = _cabi.load()
         B, T, D = inputs.shape
         if T != steps:
             raise ValueError("inputs have %d steps, expected %d" % (T, steps))
@@ -252,6 +257,8 @@ class NTMCell(object):
         if D != self.input_dim:
             raise ValueError("inputs have width %d, the cell was built for %d" % (D, self.input_dim))
         dev = self.device
+        if inputs.device != dev or inputs.dtype != torch.float32 or not inputs.is_contiguous():
+            inputs = inputs.to(dev, torch.float32).contiguous()
         shp = self._shape_struct(D)
         plan = _cabi.Plan()
         _cabi.check(lib.ntm_b200_query(C.byref(shp), B, T, C.byref(plan)), "query")
@@ -266,15 +273,29 @@ class NTMCell(object):
         if ws is None or ws.numel() < plan.workspace_bytes:
             if workspace is not None:
                 raise ValueError("workspace too small: %d < %d bytes" % (ws.numel(), plan.workspace_bytes))
+            self.finish()                                # the old workspace holds the error flag of earlier calls
             ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
             self._ws = {(B, T): ws}                      # keep only the latest geometry
         H, R, N, M = self.num_heads, self.read_head_size, self.mem_size, self.mem_dim
         CL2 = 2 * self.controller_hidden_size * self.controller_num_layers
         inner = {"M": N * M, "w": H * N, "read": R * M, "controller_state": CL2}
         want = {"M": (B, N, M), "w": (B, H, N), "read": (B, R, M), "controller_state": (B, CL2)}
+        # the reference takes NumPy state through feed_dict (test_tracker.py:284-299): accept host / NumPy
+        # state here too -- the kernels only ever see device pointers
+        conv = {}
         for k, s in want.items():
-            if tuple(state[k].shape) != s:
-                raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(state[k].shape), s))
+            v = state[k]
+            if not torch.is_tensor(v):
+                v = torch.as_tensor(np.asarray(v))
+            if tuple(v.shape) != s:
+                raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(v.shape), s))
+            if v.device != dev or v.dtype != torch.float32:
+                if continuation:
+                    raise ValueError("continuation needs the previous call's device state, got state['%s'] on %s"
+                                     % (k, v.device))
+                v = v.to(dev, torch.float32)
+            conv[k] = v
+        state = conv
         if continuation:
             if self.debug or history is not None or any(not state[k].is_contiguous() for k in want):
                 raise ValueError("continuation needs a dense state and neither debug taps nor history")
@@ -312,8 +333,9 @@ class NTMCell(object):
         lib = _cabi.load()
         ws = getattr(self, "_last_ws", None)
         if ws is not None:
-            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _cabi.check(lib.ntm_b200_finish(ws.data_ptr(), stream), "finish")
+            with torch.cuda.device(self.device):
+                stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                _cabi.check(lib.ntm_b200_finish(ws.data_ptr(), stream), "finish")
 
     def _prepare_inputs(self, inputs, ndim):
         if isinstance(inputs, np.ndarray):

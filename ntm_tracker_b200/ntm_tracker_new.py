@@ -1,8 +1,11 @@
 """LoopNTMTracker -- drop-in for the reference's batched sequence driver
 (ntm_tracker_new.py:4-64): unrolls the NTM cell over the T frames-steps of B
 independent sequences.  The reference does it with tf.while_loop + TensorArrays
-(one graph dispatch per op per step); here the whole loop is ONE persistent CUDA
-kernel call through the C ABI (ntm_b200_forward_seq).
+(one graph dispatch per op per step); here the whole loop is ONE call through the
+C ABI (ntm_b200_forward_seq), which runs it in one of two ways:
+small batches as ONE persistent kernel that keeps every sequence's memory in shared
+memory for all T steps; large batches (BASELINE's 4096 sequences) in streaming mode,
+all sequences in lockstep with a few fused kernels per timestep and the memories in HBM.
 """
 import numpy as np
 import torch
@@ -17,6 +20,29 @@ class LoopNTMTracker(object):
         self.initializer = initializer
         self.sequence_length = sequence_length
         self.final_state = None
+        self.history = None
+
+    # The reference's loop also fills TensorArrays Ms / ws / reads with the memory, weightings and read
+    # vectors AFTER every step (ntm_tracker_new.py:22-26,57-61; their stacking into the return value is
+    # commented out there, :46-49, as are the summaries that used them, direct_offset_output.py:549-575).
+    # Set record_history = True to get them: after a call, ``tracker.history`` holds time-major
+    # {'Ms': [T,B,N,M], 'ws': [T,B,H,N], 'reads': [T,B,R,M]} device tensors (the reference would stack
+    # them on the LAST axis: ``Ms.permute(1, 2, 3, 0)``).  Costs T copies of the state in HBM, like the
+    # reference's swap_memory TensorArrays.
+    record_history = False
+
+    def _history_buffers(self, B, T):
+        cell, dev = self.cell, self.cell.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        N, M, H, R = cell.mem_size, cell.mem_dim, cell.num_heads, cell.read_head_size
+        return {"M_prev": torch.empty(T + 1, B, N, M, **f32), "w_prev": torch.empty(T + 1, B, H, N, **f32),
+                "read": torch.empty(T + 1, B, R * M, **f32)}
+
+    def _publish_history(self, bufs, new_state, B, T):
+        bufs["M_prev"][T].copy_(new_state["M"])       # slot t of the recording = state ENTERING step t; the
+        bufs["w_prev"][T].copy_(new_state["w"])       # last step's result is the returned state
+        self.history = {"Ms": bufs["M_prev"][1:], "ws": bufs["w_prev"][1:],
+                        "reads": bufs["read"][1:].view(T, B, self.cell.read_head_size, self.cell.mem_dim)}
 
     def __call__(self, inputs, state=None, scope=None):
         """inputs [B, T, D] batch-major -> (outputs [B,T,O], output_logits [B,T,O])
@@ -27,14 +53,15 @@ class LoopNTMTracker(object):
         ``self.final_state`` (the reference's loop_vars M, w, read, controller_state)."""
         host_in = isinstance(inputs, np.ndarray) or not inputs.is_cuda
         as_numpy = isinstance(inputs, np.ndarray)
-        if host_in and inputs.ndim == 3 and self._time_blocks(inputs) > 1:
+        if host_in and inputs.ndim == 3 and not self.record_history and self._time_blocks(inputs) > 1:
             if inputs.shape[1] != self.sequence_length:
                 raise ValueError("inputs have %d steps but sequence_length is %d" % (inputs.shape[1], self.sequence_length))
             if self.cell.input_dim is None:
                 self.cell.build(inputs.shape[2], self.initializer)
             state = state or self.cell.zero_state(inputs.shape[0], self.initializer)
             return self._call_host_time_pipelined(inputs, state, self._time_blocks(inputs))
-        if host_in and inputs.ndim == 3 and self._pipeline_chunks(inputs.shape[0], inputs.shape[1]) > 1:
+        if host_in and inputs.ndim == 3 and not self.record_history and \
+                self._pipeline_chunks(inputs.shape[0], inputs.shape[1]) > 1:
             x = None
             B, T, D = inputs.shape
         else:
@@ -47,9 +74,13 @@ class LoopNTMTracker(object):
         state = state or self.cell.zero_state(B, self.initializer)
         if x is None:
             return self._call_host_pipelined(inputs, state, as_numpy)
-        logits, outputs, new_state, _ = self.cell._run(x, state, T)
+        bufs = self._history_buffers(B, T) if self.record_history else None
+        logits, outputs, new_state, _ = self.cell._run(x, state, T, history=bufs)
         self.final_state = new_state
+        if bufs is not None:
+            self._publish_history(bufs, new_state, B, T)
         if host_in:
+            self.cell.finish()          # the call synchronises here anyway: surface device-side failures
             outputs, logits = outputs.cpu(), logits.cpu()
             if as_numpy:
                 outputs, logits = outputs.numpy(), logits.numpy()
@@ -118,7 +149,15 @@ class LoopNTMTracker(object):
                                           continuation=(i > 0 and not cell.debug))
             outs.append(out); logs.append(lg)
         self.final_state = state
-        return torch.cat(outs, 1).cpu(), torch.cat(logs, 1).cpu()
+        out_d, log_d = torch.cat(outs, 1), torch.cat(logs, 1)
+        # results leave through page-locked buffers (torch's caching host allocator: no cudaHostAlloc per
+        # call) as two asynchronous copies and ONE synchronisation, which also checks the error flag
+        out_h = torch.empty(out_d.shape, dtype=torch.float32, pin_memory=True)
+        log_h = torch.empty(log_d.shape, dtype=torch.float32, pin_memory=True)
+        out_h.copy_(out_d, non_blocking=True)
+        log_h.copy_(log_d, non_blocking=True)
+        cell.finish()
+        return out_h, log_h
 
     # Number of batch chunks a host-resident call is split into so that the host->device copy of
     # chunk i+1 overlaps the kernels of chunk i (sequences are independent, so any split is exact).
@@ -161,6 +200,7 @@ class LoopNTMTracker(object):
             st = {k: v[lo:hi] for k, v in state.items()}
             lg, out, ns, _ = cell._run(xd.contiguous(), st, T)
             outs.append(out); logs.append(lg); states.append(ns)
+        cell.finish()
         outputs, logits = torch.cat(outs, 0).cpu(), torch.cat(logs, 0).cpu()
         self.final_state = {k: torch.cat([s_[k] for s_ in states], 0) for k in states[0]}
         if as_numpy:

@@ -163,5 +163,6 @@ class NTMTrainer(object):
 
     def train_step(self, inputs, targets, gather=None):
         loss, grads = self.loss_and_grads(inputs, targets, gather)
-        gnorm = self.apply_gradients(grads)
+        gnorm = self.apply_gradients(grads)     # synchronises (returns the host value of the global norm)
+        self.cell.finish()                      # ... so device-side failures of the forward surface here
         return loss, gnorm
