@@ -302,7 +302,7 @@ def main():
 
     def one_step(x=None):
         if training:      # forward (with history) + backward + gradient all-reduce + clip + RMSProp
-            last_loss[0], _ = trainer.train_step(x_dev if x is None else x, targets)
+            last_loss[0], _ = trainer.train_step(x_dev if x is None else x, targets, sync=False)
         else:
             trk(x_dev if x is None else x, state)
 

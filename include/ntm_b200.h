@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define NTM_B200_ABI_VERSION 1
+#define NTM_B200_ABI_VERSION 2
 #define NTM_B200_MAX_LAYERS 16
 #define NTM_B200_MAX_READ_HEADS 4
 #define NTM_B200_MAX_WRITE_HEADS 3
@@ -225,6 +225,70 @@ int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, const float* 
                                     const float* z, int64_t z_stride, const float* c_prev,
                                     const float* c_new, int64_t c_stride, float* dc, float* dz,
                                     int64_t dz_stride, void* stream);
+
+/* ---- training step (BASELINE configs[4]; direct_offset_output.py:581-626) -------------------------------- */
+
+/* Gradients w.r.t. the trainable variables, same layout as ntm_b200_weights plus the three init_state
+ * variables (ntm_cell.py:292-306).  Caller-owned device buffers (typically views into ONE flat buffer, so that
+ * a single NCCL all-reduce and a single optimizer pass cover everything).  init_* may be NULL (skipped). */
+typedef struct ntm_b200_grads {
+  float* lstm_w[NTM_B200_MAX_LAYERS];
+  float* lstm_b[NTM_B200_MAX_LAYERS];
+  float* addr_w;
+  float* addr_b;
+  float* out_w;
+  float* out_b;
+  float* init_M;     /* [N, M]   through tanh    */
+  float* init_w;     /* [R+W, N] through sigmoid */
+  float* init_read;  /* [R, M]   through tanh    */
+} ntm_b200_grads;
+
+/* Loss of the tracker and its gradient w.r.t. the logits (direct_offset_output.py:581-606):
+ * y = tanh(logits[:, steps[g], :]); loss = tf.nn.l2_loss(y - targets) = 0.5 * sum (y - targets)^2.
+ * logits [B,T,O]; targets [B,G,O]; gather_steps: HOST array of G <= 64 timesteps; loss_out: device scalar;
+ * dlogits [B,T,O] receives dLoss/dlogits (zero at the steps that do not enter the loss).  One kernel,
+ * fixed-order reduction. */
+int32_t ntm_b200_offset_loss(const float* logits, const float* targets, const int32_t* gather_steps,
+                             int32_t num_gather, int64_t batch, int64_t steps, int32_t output_dim,
+                             float* loss_out, float* dlogits, void* stream);
+
+/* Workspace the backward pass needs for this geometry (device bytes). */
+int64_t ntm_b200_backward_workspace_bytes(const ntm_b200_shape* shape, int64_t batch, int64_t steps);
+
+/* The whole backward pass through the unrolled loop -- what tf.gradients(loss, tf.trainable_variables())
+ * derives op by op in the reference (direct_offset_output.py:611-613) -- as ONE call: the reverse-time loop
+ * runs inside the library (per step: the fused memory/addressing backward kernel, the LSTM gate backward and
+ * the two data-gradient GEMMs on the tensor cores), then the weight gradients as large-K tcgen05 GEMMs over
+ * all (t, b), the bias gradients and the init_state gradients.  `history` = what ntm_b200_forward_seq_train
+ * recorded for the same inputs (all seven buffers); `dlogits` [B,T,O] from ntm_b200_offset_loss (or any other
+ * loss); `state0` = the state the forward started from (zero_state: its stride-0 tensors hold tanh / sigmoid /
+ * tanh of the init_state variables, which is what their gradient needs; per-sequence initial states get no
+ * init_state gradient).  No cuBLAS, no host synchronisation; gradients are written, not accumulated. */
+int32_t ntm_b200_backward_seq(const ntm_b200_shape* shape, const ntm_b200_weights* weights, const void* packed,
+                              int64_t batch, int64_t steps, const float* inputs,
+                              const ntm_b200_history* history, const float* dlogits,
+                              const ntm_b200_state* state0, const ntm_b200_grads* grads, void* workspace,
+                              int64_t workspace_bytes, void* stream);
+
+/* tf.clip_by_global_norm(grads, clip_norm) + RMSPropOptimizer(lr, decay, momentum, epsilon).apply_gradients
+ * (direct_offset_output.py:606-626) fused over flat buffers of n floats: global norm (two-stage fixed-order
+ * reduction), then ONE pass  g *= clip_norm / max(norm, clip_norm);  rms = decay*rms + (1-decay)*g*g;
+ * mom = momentum*mom + lr*g/sqrt(rms + epsilon);  param -= mom.  `grads` holds the (all-reduced) gradient,
+ * `scratch` >= 4 KiB of device memory, gnorm_out a device scalar (the unclipped global norm).  TF slot
+ * initialisation is the caller's: rms = 1, mom = 0. */
+int32_t ntm_b200_rmsprop_step(float* params, const float* grads, float* rms, float* mom, int64_t n,
+                              float learning_rate, float decay, float momentum, float epsilon, float clip_norm,
+                              float* gnorm_out, void* scratch, void* stream);
+
+/* out[r, j] = sum_k a[r*lda + k] * b[j*ldb + k]  (A @ B^T; fp32 in, fp32 out, ~fp32 accuracy through the
+ * 3-term bf16 operand split on the tensor cores): the tile-record tcgen05 GEMM the backward pass is built from
+ * (csrc/ntm_b200_gemm_tiles.cuh), exposed on plain row-major operands so that it can be tested and reused on
+ * its own.  kslices >= 1 = K slices summed in slice order (deterministic).  Replaces the MatMul gradient ops
+ * TensorFlow derives for ntm_cell.py:101-105,124-130,220. */
+int64_t ntm_b200_gemm_nt_workspace_bytes(int64_t nrows, int64_t ncols, int64_t K, int32_t kslices);
+int32_t ntm_b200_gemm_nt(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
+                         int64_t nrows, int64_t ncols, int64_t K, int32_t kslices, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 
 /* NTMCell.__call__ (ntm_cell.py:53-253): one step, inputs [B,D], logits/outputs
  * [B,O].  The serve path's unit of work (test_tracker.py:284-299). */

@@ -40,6 +40,12 @@ class History(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("M_prev", "w_prev", "params", "z", "c", "h", "read")]
 
 
+class Grads(C.Structure):
+    _fields_ = [("lstm_w", C.c_void_p * MAX_LAYERS), ("lstm_b", C.c_void_p * MAX_LAYERS),
+                ("addr_w", C.c_void_p), ("addr_b", C.c_void_p), ("out_w", C.c_void_p), ("out_b", C.c_void_p),
+                ("init_M", C.c_void_p), ("init_w", C.c_void_p), ("init_read", C.c_void_p)]
+
+
 class Plan(C.Structure):
     _fields_ = [("cluster_size", C.c_int32), ("rows_per_cta", C.c_int32),
                 ("sequences_resident", C.c_int32), ("threads_per_cta", C.c_int32),
@@ -78,6 +84,18 @@ SYMBOLS = {
     "ntm_b200_lstm_backward_step": (C.c_int32, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_int64, C.c_void_p]),
+    "ntm_b200_offset_loss": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int64,
+                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ntm_b200_backward_workspace_bytes": (C.c_int64, [C.POINTER(Shape), C.c_int64, C.c_int64]),
+    "ntm_b200_backward_seq": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.POINTER(History), C.c_void_p, C.POINTER(State),
+                                          C.POINTER(Grads), C.c_void_p, C.c_int64, C.c_void_p]),
+    "ntm_b200_rmsprop_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                          C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "ntm_b200_gemm_nt_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
+    "ntm_b200_gemm_nt": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ntm_b200_step": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p, C.c_int64,
                                   C.c_void_p, C.POINTER(State), C.POINTER(State), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

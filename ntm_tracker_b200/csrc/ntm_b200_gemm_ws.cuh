@@ -59,7 +59,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(umma::smem_u32(dst)), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
+static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a) {
   using namespace umma;
   extern __shared__ __align__(16) uint8_t ws_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -249,7 +249,7 @@ __device__ __forceinline__ void store_split8(uint8_t* tiles, int KAtot, long lon
 // ---- packing kernels ----
 // fp32 [rows, K] (row stride ld) -> operand tiles [row block][KAtot][hi | lo]; rows / k beyond the matrix
 // are written as zeros so the whole record is valid MMA input.  One thread per 8 consecutive k.
-__global__ void pack_act_tiles_kernel(const float* __restrict__ x, long long rows, int K, int ld, uint8_t* tiles,
+static __global__ void pack_act_tiles_kernel(const float* __restrict__ x, long long rows, int K, int ld, uint8_t* tiles,
                                       int KAtot, int k_off) {
   const long long nrb = (rows + 127) / 128;
   const int KAsrc = (K + 63) / 64;
@@ -280,7 +280,7 @@ __global__ void pack_act_tiles_kernel(const float* __restrict__ x, long long row
 }
 
 // W [K, ncols] (row stride ldw) -> per (tile, slice): hi words [128 cols][KA*32], lo swizzled images [KA][16 KiB].
-__global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int K, int ncols, int ldw, uint32_t* whi,
+static __global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int K, int ncols, int ldw, uint32_t* whi,
                                          uint8_t* wlo, int ntiles, int kslices, int KA, int wlo_words) {
   const long long total = (long long)ntiles * kslices * 128 * KA * 8;      // 8-k chunks
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -341,7 +341,7 @@ inline bool plan_ok(const Plan& p, int nsm) { return p.ntiles * p.kslices <= nsm
 
 inline int smem_bytes(const Plan& p) { return 1024 + (p.wlo_tmem ? 0 : p.KA * ATOM_BYTES) + p.nslot * REC_BYTES; }
 
-inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi, const uint8_t* wlo, const float* bias,
+static inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi, const uint8_t* wlo, const float* bias,
                           float* out, int ldo, long long slab, long long rows, cudaStream_t stream) {
   Args a{};
   a.act = act; a.whi = whi; a.wlo = wlo; a.bias = bias; a.out = out; a.rows = rows; a.slab = slab; a.ldo = ldo;

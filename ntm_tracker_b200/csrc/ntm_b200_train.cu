@@ -22,6 +22,7 @@
 
 #include "ntm_b200.h"
 #include "ntm_b200_params.h"
+#include "ntm_b200_train.h"
 
 namespace ntm_b200 {
 namespace train {
@@ -35,7 +36,10 @@ struct BwdParams {
   const float* M_prev;        // [B, N, M]
   const float* w_prev;        // [B, H, N]
   const float* raw;           // [B, PO4]
-  const float* d_read;        // [B, R, M]
+  const float* d_read;        // [B, R, M], sequences sdr floats apart
+  long long sdr;
+  const float* dlogits;       // [B, T, O] gradient w.r.t. the logits (fills the logit slots of d_raw), or null
+  int T, t, O;
   const float* d_w;           // [B, H, N]
   float* dM;                  // [B, N, M] in: dL/dM_t, out: dL/dM_{t-1}
   float* d_w_prev;            // [B, H, N]
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
     float4 dr4[R], e4[W], a4[W], dea[W], daa[W];
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      dr4[r] = cvalid ? ld4(q.d_read + ((size_t)b * R + r) * M, M, 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dr4[r] = cvalid ? ld4(q.d_read + (size_t)b * q.sdr + (size_t)r * M, M, 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < W; ++h) {
       e4[h] = cvalid ? *reinterpret_cast<const float4*>(eS + h * M4 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -476,12 +480,18 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
     draw[offGam + tid] = sDgam[tid] * sigmoid_f(raw[offGam + tid]);
     for (int s = 0; s < S; ++s) draw[offS + tid * S + s] = sDsw[tid * SMAX + s];
   }
-  for (int i = q.P + tid; i < q.PO4; i += NT) draw[i] = 0.0f;   // logit slots belong to the caller
+  // logit slots: the loss gradient w.r.t. this step's logits when the caller hands it over (the projection
+  // h @ [W_addr | W_out] is ONE GEMM, so its backward wants them in the same row), else zero
+  for (int i = q.P + tid; i < q.PO4; i += NT) {
+    const int o = i - q.P;
+    draw[i] = (q.dlogits != nullptr && o < q.O) ? q.dlogits[((size_t)b * q.T + q.t) * q.O + o] : 0.0f;
+  }
 }
 
 // LSTM cell backward for one layer and one timestep, all sequences: elementwise over [B, C].
 // BasicLSTMCell forward (TF 1.0/1.1): c' = c*sig(f) + sig(i)*tanh(j); h' = tanh(c')*sig(o).
-__global__ void lstm_backward_kernel(int B, int C, const float* __restrict__ dh_a, const float* __restrict__ dh_b,
+__global__ void lstm_backward_kernel(int B, int C, const float* __restrict__ dh_a, long long lda,
+                                     const float* __restrict__ dh_b, long long ldb, int nslab, long long slab,
                                      const float* __restrict__ z, long long z_stride,
                                      const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                      long long c_stride, float* __restrict__ dc, float* __restrict__ dz,
@@ -492,7 +502,9 @@ __global__ void lstm_backward_kernel(int B, int C, const float* __restrict__ dh_
     const float* zb = z + (size_t)b * z_stride;
     const float gi = sigmoid_f(zb[u]), gj = tanhf(zb[C + u]), gf = sigmoid_f(zb[2 * C + u]), go = sigmoid_f(zb[3 * C + u]);
     const float cp = c_prev[(size_t)b * c_stride + u], tc = tanhf(c_new[(size_t)b * c_stride + u]);
-    const float dh = dh_a[i] + (dh_b ? dh_b[i] : 0.0f);
+    float dh = dh_a != nullptr ? dh_a[(size_t)b * lda + u] : 0.0f;
+    if (dh_b != nullptr)
+      for (int s2 = 0; s2 < nslab; ++s2) dh += dh_b[(size_t)s2 * slab + (size_t)b * ldb + u];   // K-slice slabs, slice order
     const float dct = dc[i] + dh * go * (1.0f - tc * tc);
     float* dzb = dz + (size_t)b * dz_stride;
     dzb[u] = dct * gj * gi * (1.0f - gi);
@@ -514,28 +526,11 @@ static BwdKernel select_bwd(int R, int W) {
   return table[R - 1][W - 1];
 }
 
-}  // namespace train
-}  // namespace ntm_b200
 
-extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_t batch, const float* M_prev,
-                                                 const float* w_prev, const float* raw_params,
-                                                 const float* d_read, const float* d_w, float* dM,
-                                                 float* d_w_prev, float* d_raw_params, void* stream) {
-  using namespace ntm_b200;
-  using namespace ntm_b200::train;
-  if (!s || !M_prev || !w_prev || !raw_params || !d_read || !d_w || !dM || !d_w_prev || !d_raw_params)
-    return NTM_B200_ERR_NULL_POINTER;
-  if (batch < 1 || s->mem_size < 1 || s->mem_dim < 1) return NTM_B200_ERR_BAD_SHAPE;
-  if (s->read_head_size < 1 || s->read_head_size > NTM_B200_MAX_READ_HEADS || s->write_head_size < 1 ||
-      s->write_head_size > NTM_B200_MAX_WRITE_HEADS)
-    return NTM_B200_ERR_UNSUPPORTED_HEADS;
-  if (s->shift_range < 0 || s->shift_range > NTM_B200_MAX_SHIFT_RANGE) return NTM_B200_ERR_BAD_SHIFT;
-  int dev = 0, major = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
-      major != 10) {
-    cudaGetLastError();
-    return NTM_B200_ERR_NO_DEVICE;
-  }
+int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float* M_prev, const float* w_prev,
+                           const float* raw_params, const float* d_read, long long sdr, const float* d_w, float* dM,
+                           float* d_w_prev, float* d_raw_params, const float* dlogits, int T, int t,
+                           cudaStream_t stream) {
   BwdParams q{};
   const int R = s->read_head_size, W = s->write_head_size, H = R + W;
   q.N = s->mem_size; q.M = s->mem_dim; q.M4 = (q.M + 3) / 4 * 4; q.MC = q.M4 / 4; q.Np = (q.N + 3) / 4 * 4;
@@ -546,8 +541,9 @@ extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_
   q.TPR = std::min(NT, (q.MC + 31) / 32 * 32);
   if (q.MC > NT) return NTM_B200_ERR_TOO_LARGE;
   q.RG = NT / q.TPR; q.TW = q.TPR / 32;
-  q.M_prev = M_prev; q.w_prev = w_prev; q.raw = raw_params; q.d_read = d_read; q.d_w = d_w; q.dM = dM;
+  q.M_prev = M_prev; q.w_prev = w_prev; q.raw = raw_params; q.d_read = d_read; q.sdr = sdr; q.d_w = d_w; q.dM = dM;
   q.d_w_prev = d_w_prev; q.d_raw = d_raw_params;
+  q.dlogits = dlogits; q.T = T; q.t = t; q.O = s->output_dim;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
   q.oK = take(H * q.M4); q.oKhat = take(H * q.M4); q.oKc = take(H * q.M4); q.oE = take(W * q.M4); q.oA = take(W * q.M4);
@@ -565,9 +561,53 @@ extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_
     cudaGetLastError();
     return NTM_B200_ERR_CUDA;
   }
-  k<<<(unsigned)batch, NT, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  k<<<(unsigned)batch, NT, smem, stream>>>(q);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+}
+
+int launch_lstm_backward(long long batch, int hidden, const float* dh_a, long long lda, const float* dh_b, long long ldb,
+                         int nslab, long long slab, const float* z, long long z_stride, const float* c_prev,
+                         const float* c_new, long long c_stride, float* dc, float* dz, long long dz_stride,
+                         cudaStream_t stream) {
+  const int total = (int)(batch * hidden);
+  const int blocks = std::min((total + 255) / 256, B200_SMS * 8);
+  lstm_backward_kernel<<<blocks, 256, 0, stream>>>((int)batch, hidden, dh_a, lda, dh_b, ldb, nslab, slab, z, z_stride,
+                                                  c_prev, c_new, c_stride, dc, dz, dz_stride);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+}
+
+}  // namespace train
+}  // namespace ntm_b200
+
+namespace {
+bool on_sm100() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      major != 10) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_t batch, const float* M_prev,
+                                                 const float* w_prev, const float* raw_params,
+                                                 const float* d_read, const float* d_w, float* dM,
+                                                 float* d_w_prev, float* d_raw_params, void* stream) {
+  if (!s || !M_prev || !w_prev || !raw_params || !d_read || !d_w || !dM || !d_w_prev || !d_raw_params)
+    return NTM_B200_ERR_NULL_POINTER;
+  if (batch < 1 || s->mem_size < 1 || s->mem_dim < 1) return NTM_B200_ERR_BAD_SHAPE;
+  if (s->read_head_size < 1 || s->read_head_size > NTM_B200_MAX_READ_HEADS || s->write_head_size < 1 ||
+      s->write_head_size > NTM_B200_MAX_WRITE_HEADS)
+    return NTM_B200_ERR_UNSUPPORTED_HEADS;
+  if (s->shift_range < 0 || s->shift_range > NTM_B200_MAX_SHIFT_RANGE) return NTM_B200_ERR_BAD_SHIFT;
+  if (!on_sm100()) return NTM_B200_ERR_NO_DEVICE;
+  return ntm_b200::train::launch_memory_backward(s, batch, M_prev, w_prev, raw_params, d_read,
+                                                 (long long)s->read_head_size * s->mem_dim, d_w, dM, d_w_prev,
+                                                 d_raw_params, nullptr, 1, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, const float* dh_a, const float* dh_b,
@@ -576,16 +616,7 @@ extern "C" int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, co
                                                int64_t dz_stride, void* stream) {
   if (!dh_a || !z || !c_prev || !c_new || !dc || !dz) return NTM_B200_ERR_NULL_POINTER;
   if (batch < 1 || hidden < 1 || batch * (int64_t)hidden > (1ll << 30)) return NTM_B200_ERR_BAD_SHAPE;
-  int dev = 0, major = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
-      major != 10) {
-    cudaGetLastError();
-    return NTM_B200_ERR_NO_DEVICE;
-  }
-  const int total = (int)(batch * hidden);
-  const int blocks = std::min((total + 255) / 256, ntm_b200::B200_SMS * 8);
-  ntm_b200::train::lstm_backward_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      (int)batch, hidden, dh_a, dh_b, z, z_stride, c_prev, c_new, c_stride, dc, dz, dz_stride);
-  ntm_b200::count_launch();
-  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+  if (!on_sm100()) return NTM_B200_ERR_NO_DEVICE;
+  return ntm_b200::train::launch_lstm_backward(batch, hidden, dh_a, hidden, dh_b, hidden, 1, 0, z, z_stride, c_prev, c_new,
+                                               c_stride, dc, dz, dz_stride, static_cast<cudaStream_t>(stream));
 }

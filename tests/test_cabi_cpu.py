@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.ntm_b200_abi_version() == 1
+    assert lib.ntm_b200_abi_version() == 2
     for code in range(10):
         assert len(lib.ntm_b200_status_string(code)) > 0
     assert b"no CPU fallback" in lib.ntm_b200_status_string(7)

@@ -151,3 +151,27 @@ def test_train_step_reduces_loss_and_matches_reference_optimizer():
         got = trk.cell.variables[k].detach().cpu().numpy()
         assert np.abs(got - v).max() <= 2e-4, k
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("nrows,ncols,K,ks", [(256, 200, 3616, 15), (256, 2248, 800, 1), (70, 130, 100, 2),
+                                              (300, 800, 2048, 4), (5, 7, 9, 1)])
+def test_tile_gemm_matches_fp64_matmul(nrows, ncols, K, ks):
+    """The tcgen05 tile-record GEMM of the backward pass on its own (out = A @ B^T): pack kernels, K slices,
+    ragged edges, against a float64 matmul.  Budget: the 3-term bf16 split keeps ~2^-16 of each product."""
+    import ctypes as C
+    from ntm_tracker_b200 import _cabi
+    lib = _cabi.load()
+    g = torch.Generator().manual_seed(nrows * 7 + K)
+    a = torch.randn(nrows, K + 3, generator=g).cuda()            # padded leading dimensions
+    b = torch.randn(ncols, K + 5, generator=g).cuda()
+    out = torch.full((nrows, ncols), float("nan")).cuda()
+    need = lib.ntm_b200_gemm_nt_workspace_bytes(nrows, ncols, K, ks)
+    ws = torch.empty(need, dtype=torch.uint8).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _cabi.check(lib.ntm_b200_gemm_nt(a.data_ptr(), K + 3, b.data_ptr(), K + 5, out.data_ptr(), ncols, nrows, ncols, K,
+                                     ks, ws.data_ptr(), need, stream), "gemm_nt")
+    torch.cuda.synchronize()
+    ref = a[:, :K].double() @ b[:, :K].double().t()
+    err = float((out.double() - ref).abs().max())
+    scale = float(ref.abs().max())
+    assert err <= 2e-5 * scale, (err, scale)

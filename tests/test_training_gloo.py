@@ -28,12 +28,26 @@ def ref_grads(params, x, targets):
     return {k: v.grad.float() for k, v in ref.p.items()}
 
 
+def _numpy_update(self):
+    """Test stand-in for NTMTrainer._fused_update (the product's is a CUDA library call): the same
+    tf.clip_by_global_norm + RMSProp arithmetic (direct_offset_output.py:606-626) on the flat CPU buffers."""
+    g = self._grad
+    gn = torch.linalg.vector_norm(g)
+    g = g * (self.clip / torch.clamp(gn, min=self.clip))
+    self._rms.mul_(self.decay).addcmul_(g, g, value=1.0 - self.decay)
+    self._mom.mul_(self.momentum).add_(self.lr * g / torch.sqrt(self._rms + self.eps))
+    self._flat.sub_(self._mom)
+    self.last_gnorm.copy_(gn.reshape(1))
+
+
 def make_trainer(params):
     from ntm_tracker_b200 import LoopNTMTracker, NTMTrainer
     kw = {k: v for k, v in SHAPE.items() if k not in ("input_dim", "output_dim")}
-    trk = LoopNTMTracker(6, 2, device="cpu", **kw)     # variables on the CPU: only the optimizer runs here
+    trk = LoopNTMTracker(6, 2, device="cpu", **kw)     # variables on the CPU: only the host-side logic runs here
     trk.cell.load_reference_weights(params)
-    return NTMTrainer(trk, learning_rate=1e-2)
+    trainer = NTMTrainer(trk, learning_rate=1e-2)
+    trainer._fused_update = _numpy_update.__get__(trainer)          # flat buffers, all-reduce, views: the product's
+    return trainer
 
 
 def data():
