@@ -159,7 +159,13 @@ int32_t ntm_b200_forward_seq_continue(const ntm_b200_shape* shape, const ntm_b20
  *                            PO4 = round_up(P + O, 4), layout of ntm_cell.py:126-130 then logits
  *   z        [T, B, L, 4, C] LSTM gate pre-activations i, j, f, o of step t
  *   c, h     [T+1, B, L, C]  LSTM cell / hidden state: slot 0 = initial, slot t+1 = after step t
- *   read     [T+1, B, R*M]   read vectors: slot 0 = initial, slot t+1 = produced by step t */
+ *   read     [T+1, B, R*M]   read vectors: slot 0 = initial, slot t+1 = produced by step t
+ *   sim      [T, B, R+W, N]  (optional) un-normalised similarities of step t: sum_d tanh(k)[h,d] * cn[d] *
+ *                            M_prev[n,d]  (the key's own 1/|k| not yet applied, ops.py:152-156)
+ *   cn       [T, B, M]       (optional) inverse column norms of M_prev[t] (tf.nn.l2_normalize over N,
+ *                            ops.py:147-150)
+ * sim and cn are by-products of the forward pass; with both recorded the backward pass skips two of its five
+ * sweeps over the memory (it re-derives them otherwise). */
 typedef struct ntm_b200_history {
   float* M_prev;
   float* w_prev;
@@ -168,6 +174,8 @@ typedef struct ntm_b200_history {
   float* c;
   float* h;
   float* read;
+  float* sim;
+  float* cn;
 } ntm_b200_history;
 
 /* ntm_b200_forward_seq that also records `history` (may be NULL = plain forward). */

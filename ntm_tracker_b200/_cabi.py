@@ -37,7 +37,7 @@ class State(C.Structure):
 
 
 class History(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("M_prev", "w_prev", "params", "z", "c", "h", "read")]
+    _fields_ = [(n, C.c_void_p) for n in ("M_prev", "w_prev", "params", "z", "c", "h", "read", "sim", "cn")]
 
 
 class Grads(C.Structure):

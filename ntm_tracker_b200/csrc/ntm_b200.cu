@@ -635,7 +635,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   p.logits = logits; p.outputs = outputs; p.dbg = debug_taps; p.dbgStride = hp.debug_floats;
   if (history != nullptr) {
     p.hM = history->M_prev; p.hW = history->w_prev; p.hP = history->params; p.hZ = history->z;
-    p.hC = history->c; p.hH = history->h; p.hRead = history->read;
+    p.hC = history->c; p.hH = history->h; p.hRead = history->read; p.hSim = history->sim; p.hCn = history->cn;
   }
   p.cst = reinterpret_cast<float*>(wsb + ws.off_cst); p.cst_ts = ws.cst_ts;
   p.partA = reinterpret_cast<float*>(wsb + ws.off_partA); p.partA_ts = ws.partA_ts;

@@ -362,7 +362,9 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
     float* draw = DMC + (size_t)t * B * PO4;
     st = train::launch_memory_backward(s, B, hist->M_prev + (size_t)t * B * N * M, hist->w_prev + (size_t)t * B * H * N,
                                        hist->params + (size_t)t * B * PO4, dcat[0], y.ncat[0], dwbuf[cur], dM,
-                                       dwbuf[cur ^ 1], draw, dlogits, (int)T, (int)t, stream);
+                                       dwbuf[cur ^ 1], draw, dlogits, (int)T, (int)t,
+                                       (hist->sim && hist->cn) ? hist->sim + (size_t)t * B * H * N : nullptr,
+                                       (hist->sim && hist->cn) ? hist->cn + (size_t)t * B * M : nullptr, stream);
     if (st) return st == NTM_B200_ERR_CUDA ? set_cuda_error_ext(cudaGetLastError(), "mem_backward_kernel") : st;
     cur ^= 1;
     // d_h(top) = d_raw @ [W_addr | W_out]^T, K slices into slabs

@@ -49,7 +49,7 @@ struct KParams {
   float* dbg;
   long long dbgStride;
   // training-mode history (all optional, null = not recorded); see ntm_b200_history in ntm_b200.h
-  float *hM, *hW, *hP, *hZ, *hC, *hH, *hRead;
+  float *hM, *hW, *hP, *hZ, *hC, *hH, *hRead, *hSim, *hCn;
   float* act[MAXL];                    // team 0's slice; team t at + t * act_ts[l]
   long long act_ts[MAXL];
   int actK[MAXL];

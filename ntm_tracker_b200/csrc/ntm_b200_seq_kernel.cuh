@@ -456,6 +456,10 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
       hw[i] = wprev[h * Npad + n];
     }
   }
+  if (p.hCn != nullptr && crank == 0) {  // inverse column norms of the memory entering this step
+    float* hc = p.hCn + ((size_t)t * p.B + bglob) * M;
+    for (int d = tid; d < M; d += NT) hc[d] = cn[d];
+  }
   if (p.hM != nullptr) {                 // memory entering this step (this CTA's rows)
     float* hm = p.hM + (((size_t)t * p.B + bglob) * N + row0) * M;
     for (int i = tid; i < nrows * M; i += NT) {
@@ -645,7 +649,9 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
     const int h = i / N, n = i - h * N;
     const int q = n / p.NR;
     const float* rem = cluster.map_shared_rank(simL, q);
-    simA[h * Npad + n] = rem[h * p.NR + (n - q * p.NR)];
+    const float sv = rem[h * p.NR + (n - q * p.NR)];
+    simA[h * Npad + n] = sv;
+    if (p.hSim != nullptr && crank == 0) p.hSim[((size_t)t * p.B + bglob) * H * N + i] = sv;   // un-normalised similarities
   }
   __syncthreads();
   mark_slot(prow, tmark, 11);

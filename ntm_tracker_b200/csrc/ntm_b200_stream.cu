@@ -76,6 +76,7 @@ struct MemArgs {
   uint8_t* tilesA; int KAtotA;               // controller-GEMM operand tiles (read vectors at k = r*M + d), or null
   long long B;
   long long* prof;                           // [B][8] phase timestamps (globaltimer ns) of the last launch, or null
+  float* sim_hist; float* cn_hist;           // training history of this step: [B][H][N] un-normalised similarities, [B][M] cn
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
         ra[h] = in ? rawv(offA + h * M + d) : 0.0f;
       }
       const float cnd = in ? __ldcg(cnb + d) : 0.0f;
+      if (in && a.cn_hist != nullptr) a.cn_hist[(size_t)b * M + d] = cnd;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         rv[h] = in ? tanh_f(rv[h]) : 0.0f;
@@ -238,6 +240,8 @@ __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
     }
   }
   __syncthreads();
+  if (a.sim_hist != nullptr)
+    for (int i = tid; i < H * N; i += NT) a.sim_hist[(size_t)b * H * N + i] = simS[(i / N) * Npad + (i % N)];
 
   // ---- addressing on the [H][N] weightings (ntm_cell.py:140-176): WPH warps per head ----
   {
@@ -602,6 +606,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
       for (int h = 0; h < H; ++h) ss[h] = 0.0f;
       for (int d = tid; d < M; d += NT) {
         const float cnd = cnS[d];
+        if (a.cn_hist != nullptr) a.cn_hist[(size_t)b * M + d] = cnd;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           const float kv = tanh_f(raw[h * M + d]);
@@ -733,6 +738,8 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     }
     __syncthreads();
     MEM_PROF(3);
+    if (a.sim_hist != nullptr)     // training history: un-normalised similarities (here Npad == N)
+      for (int i = tid; i < H * N; i += NT) a.sim_hist[(size_t)b * H * N + i] = simS[i];
 
     // ---- addressing (ntm_cell.py:140-176): one warp (WPH warps when there are spares) per head.  Every
     //      sweep over the head's N entries handles four entries per lane at a time -- loads, then math,
@@ -1536,6 +1543,8 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       } else {
         ma.w_in = out->w; ma.sw_in = out->stride_w; ma.w_out = out->w; ma.sw_out = out->stride_w;
       }
+      ma.sim_hist = (hist && hist->sim) ? hist->sim + (size_t)t * B * H * N : nullptr;
+      ma.cn_hist = (hist && hist->cn) ? hist->cn + (size_t)t * B * M : nullptr;
       if (hist && hist->read) {
         ma.read_out = hist->read + (size_t)(t + 1) * B * R * M; ma.s_read = (long long)R * M;
       } else {

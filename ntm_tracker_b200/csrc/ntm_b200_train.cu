@@ -27,12 +27,14 @@
 namespace ntm_b200 {
 namespace train {
 
-constexpr int NT = 512;
+constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
 
 struct BwdParams {
   int N, M, M4, MC, Np, S, shift0, R, W, H, P, PO4, write_first;
   int TPR, RG, TW;            // threads per row (multiple of 32), row groups, warps per row
+  const float* sim_hist;      // [B, H, N] un-normalised similarities the forward pass recorded, or null
+  const float* cn_hist;       // [B, M] inverse column norms the forward pass recorded, or null
   const float* M_prev;        // [B, N, M]
   const float* w_prev;        // [B, H, N]
   const float* raw;           // [B, PO4]
@@ -45,7 +47,7 @@ struct BwdParams {
   float* d_w_prev;            // [B, H, N]
   float* d_raw;               // [B, PO4]
   // shared-memory offsets (floats)
-  int oK, oKhat, oKc, oE, oA, oCn, oCok, oDkh, oDe, oDa, oCt;
+  int oK, oKhat, oE, oA, oCn, oCok, oDkh, oDe, oDa, oCt;
   int oSim, oWc, oWg, oWt, oPw, oW, oDw, oDsim, oWp;
   int oRow, oCol, oSc;
 };
@@ -83,8 +85,29 @@ __device__ __forceinline__ void st4(float* base, int M, int d0, const float4& v)
   if (d0 + 3 < M) base[d0 + 3] = v.w;
 }
 
+// Transposing warp reduction of NV <= 32 per-lane partial sums: at offset o a lane keeps one half of its value
+// list and receives the partner's sums of that half; lane L ends with the warp total of value L (fixed order).
+// 31 shuffles for up to 32 values instead of 5 per value.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float send = up ? v[j] : v[j + o];
+      const float keep = up ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// Thread mapping: thread = (16-byte column chunk c = tid % TPR, row group rg = tid / TPR); a warp covers 32
+// consecutive chunks of one row group (TW = TPR / 32 warps per row).  Every sweep over the memory handles a
+// QUAD of four consecutive rows per iteration (four independent loads in flight; 4 * H <= 28 row partials per
+// lane, combined by one transposing reduction per quad).  Two CTAs per SM.
 template <int R, int W>
-__global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) {
+__global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) {
   constexpr int H = R + W;
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -93,14 +116,15 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
   const int c = tid % q.TPR, rg = tid / q.TPR;      // column chunk, row group
   const bool cvalid = c < MC && rg < q.RG;
   const int wrow = (tid % q.TPR) >> 5;              // warp index within the row
-  float* kS = sm + q.oK;   float* khat = sm + q.oKhat; float* kc = sm + q.oKc;
+  const int NQ = (N + 3) >> 2;                      // quads of rows
+  float* kS = sm + q.oK;   float* khat = sm + q.oKhat;
   float* eS = sm + q.oE;   float* aS = sm + q.oA;      float* cn = sm + q.oCn;  float* cok = sm + q.oCok;
   float* dkh = sm + q.oDkh; float* deS = sm + q.oDe;   float* daS = sm + q.oDa; float* ct = sm + q.oCt;
   float* sim = sm + q.oSim; float* wc = sm + q.oWc; float* wg = sm + q.oWg; float* wt = sm + q.oWt;
   float* pw = sm + q.oPw;   float* wv = sm + q.oW;  float* dw = sm + q.oDw; float* dsim = sm + q.oDsim;
   float* wp = sm + q.oWp;
   float* rowbuf = sm + q.oRow;                       // [N][TW][H]
-  float* colbuf = sm + q.oCol;                       // [RG][NQ][M4]
+  float* colbuf = sm + q.oCol;                       // [RG][NQC][M4]
   float* sc = sm + q.oSc;                            // scalars
   float* sBeta = sc, *sG = sc + H, *sGam = sc + 2 * H, *sRs = sc + 3 * H, *sKok = sc + 4 * H,
         *sSw = sc + 5 * H, *sDsw = sc + 5 * H + H * SMAX, *sDbeta = sc + 5 * H + 2 * H * SMAX,
@@ -110,6 +134,7 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
   const float* raw = q.raw + (size_t)b * q.PO4;
   const int offBeta = H * M, offG = offBeta + H, offS = offG + H, offGam = offS + S * H,
             offE = offGam + H, offA = offE + M * W;
+  const bool recorded = q.sim_hist != nullptr && q.cn_hist != nullptr;
 
   // ---- (1) activations of the recorded raw head parameters ----
   for (int i = tid; i < H * M4; i += NT) {
@@ -135,11 +160,21 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
     const int h = i / N, n = i - h * N;
     wp[h * Np + n] = q.w_prev[(size_t)b * H * N + i];
     dw[h * Np + n] = q.d_w[(size_t)b * H * N + i];
+    if (recorded) sim[h * Np + n] = q.sim_hist[(size_t)b * H * N + i];   // un-normalised: times 1/|k| below
+  }
+  if (recorded) {
+    // inverse column norms as the forward pass computed them; the clamp of tf.nn.l2_normalize
+    // (sum of squares <= 1e-12, ops.py:147-150) shows as cn >= 1e6 and cuts the gradient
+    for (int d = tid; d < M4; d += NT) {
+      const float v = d < M ? q.cn_hist[(size_t)b * M + d] : 0.0f;
+      cn[d] = v;
+      cok[d] = (d < M && v < 0.999e6f) ? 1.0f : 0.0f;
+    }
   }
   __syncthreads();
 
-  // ---- (2) F1: column sums of squares -> cn ----
-  {
+  // ---- (2) F1: column sums of squares -> cn (only when the forward pass did not record them) ----
+  if (!recorded) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cvalid)
       for (int n = rg; n < N; n += q.RG) {
@@ -148,13 +183,13 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
         acc.z = fmaf(m.z, m.z, acc.z); acc.w = fmaf(m.w, m.w, acc.w);
       }
     if (cvalid) *reinterpret_cast<float4*>(colbuf + (size_t)rg * M4 + 4 * c) = acc;
-  }
-  __syncthreads();
-  for (int d = tid; d < M4; d += NT) {
-    float s = 0.0f;
-    for (int r2 = 0; r2 < q.RG; ++r2) s += colbuf[(size_t)r2 * M4 + d];
-    cn[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
-    cok[d] = (s > 1e-12f) ? 1.0f : 0.0f;
+    __syncthreads();
+    for (int d = tid; d < M4; d += NT) {
+      float s = 0.0f;
+      for (int r2 = 0; r2 < q.RG; ++r2) s += colbuf[(size_t)r2 * M4 + d];
+      cn[d] = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+      cok[d] = (s > 1e-12f) ? 1.0f : 0.0f;
+    }
   }
   for (int h = warp; h < H; h += NWARP) {
     float s = 0.0f;
@@ -163,39 +198,53 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
     if (lane == 0) { sRs[h] = 1.0f / sqrtf(fmaxf(s, 1e-12f)); sKok[h] = (s > 1e-12f) ? 1.0f : 0.0f; }
   }
   __syncthreads();
-  for (int i = tid; i < H * M4; i += NT) {
-    const int h = i / M4, d = i - h * M4;
-    khat[i] = kS[i] * sRs[h];
-    kc[i] = khat[i] * cn[d];
-  }
+  for (int i = tid; i < H * M4; i += NT) khat[i] = kS[i] * sRs[i / M4];
+  if (recorded)
+    for (int i = tid; i < H * N; i += NT) {
+      const int h = i / N, n = i - h * N;
+      sim[h * Np + n] *= sRs[h];
+    }
   __syncthreads();
 
-  // ---- (3) F2: similarities (row reductions) ----
-  for (int n0 = 0; n0 < N; n0 += q.RG) {
-    const int n = n0 + rg;
-    float part[H];
+  // ---- (3) F2: similarities (row reductions), only when not recorded ----
+  if (!recorded) {
+    float4 kc4[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) part[h] = 0.0f;
-    if (cvalid && n < N) {
-      const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
-#pragma unroll
-      for (int h = 0; h < H; ++h) part[h] = dot4(m, *reinterpret_cast<const float4*>(kc + h * M4 + 4 * c));
+    for (int h = 0; h < H; ++h) {
+      kc4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cvalid) {
+        const float4 kh = *reinterpret_cast<const float4*>(khat + h * M4 + 4 * c);
+        const float4 c4 = *reinterpret_cast<const float4*>(cn + 4 * c);
+        kc4[h] = make_float4(kh.x * c4.x, kh.y * c4.y, kh.z * c4.z, kh.w * c4.w);
+      }
     }
+    for (int q0 = 0; q0 < NQ; q0 += q.RG) {
+      const int n0 = 4 * (q0 + rg);
+      float v[32];
 #pragma unroll
-    for (int h = 0; h < H; ++h) part[h] = warp_sum(part[h]);
-    if (lane == 0 && rg < q.RG && n < N) {
+      for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+      if (cvalid && n0 < N) {
+        float4 m[4];
 #pragma unroll
-      for (int h = 0; h < H; ++h) rowbuf[((size_t)n * q.TW + wrow) * H + h] = part[h];
+        for (int i = 0; i < 4; ++i) m[i] = ld4(Mb + (size_t)min(n0 + i, N - 1) * M, M, 4 * c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int h = 0; h < H; ++h) v[i * H + h] = dot4(m[i], kc4[h]);
+      }
+      const float tot = warp_transpose_sum(v, lane);
+      const int vi = lane / H, vh = lane - vi * H;
+      if (lane < 4 * H && rg < q.RG && n0 + vi < N) rowbuf[((size_t)(n0 + vi) * q.TW + wrow) * H + vh] = tot;
     }
+    __syncthreads();
+    for (int i = tid; i < H * N; i += NT) {
+      const int h = i / N, n = i - h * N;
+      float s = 0.0f;
+      for (int w2 = 0; w2 < q.TW; ++w2) s += rowbuf[((size_t)n * q.TW + w2) * H + h];
+      sim[h * Np + n] = s;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = tid; i < H * N; i += NT) {
-    const int h = i / N, n = i - h * N;
-    float s = 0.0f;
-    for (int w2 = 0; w2 < q.TW; ++w2) s += rowbuf[((size_t)n * q.TW + w2) * H + h];
-    sim[h * Np + n] = s;
-  }
-  __syncthreads();
 
   // ---- (4) forward weightings, one warp per head (ntm_cell.py:140-176) ----
   for (int h = warp; h < H; h += NWARP) {
@@ -245,60 +294,69 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
       dea[h] = make_float4(0.f, 0.f, 0.f, 0.f);
       daa[h] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int n0 = 0; n0 < N; n0 += q.RG) {
-      const int n = n0 + rg;
-      float part[H];
+    for (int q0 = 0; q0 < NQ; q0 += q.RG) {
+      const int n0 = 4 * (q0 + rg);
+      float v[32];
 #pragma unroll
-      for (int h = 0; h < H; ++h) part[h] = 0.0f;
-      if (cvalid && n < N) {
-        const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
-        const float4 dmn = ld4(dMb + (size_t)n * M, M, 4 * c);
-        float ww[W];
-        float4 F[W];
-        float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+      if (cvalid && n0 < N) {
+        float4 m4[4], dm4[4];
 #pragma unroll
-        for (int h = 0; h < W; ++h) {
-          ww[h] = wv[(R + h) * Np + n];
-          F[h] = make_float4(1.0f - ww[h] * e4[h].x, 1.0f - ww[h] * e4[h].y, 1.0f - ww[h] * e4[h].z, 1.0f - ww[h] * e4[h].w);
-          E.x *= F[h].x; E.y *= F[h].y; E.z *= F[h].z; E.w *= F[h].w;
-          A.x = fmaf(ww[h], a4[h].x, A.x); A.y = fmaf(ww[h], a4[h].y, A.y);
-          A.z = fmaf(ww[h], a4[h].z, A.z); A.w = fmaf(ww[h], a4[h].w, A.w);
+        for (int i = 0; i < 4; ++i) {
+          const int n = min(n0 + i, N - 1);
+          m4[i] = ld4(Mb + (size_t)n * M, M, 4 * c);
+          dm4[i] = ld4(dMb + (size_t)n * M, M, 4 * c);
         }
-        const float4 mn = make_float4(fmaf(m.x, E.x, A.x), fmaf(m.y, E.y, A.y), fmaf(m.z, E.z, A.z), fmaf(m.w, E.w, A.w));
-        const float4 mu = q.write_first ? mn : m;
-        float4 dmu = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float wr = wv[r * Np + n];
-          dmu.x = fmaf(wr, dr4[r].x, dmu.x); dmu.y = fmaf(wr, dr4[r].y, dmu.y);
-          dmu.z = fmaf(wr, dr4[r].z, dmu.z); dmu.w = fmaf(wr, dr4[r].w, dmu.w);
-          part[r] = dot4(dr4[r], mu);
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + i;
+          if (n < N) {
+            const float4 m = m4[i], dmn = dm4[i];
+            float ww[W];
+            float4 F[W];
+            float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+              ww[h] = wv[(R + h) * Np + n];
+              F[h] = make_float4(1.0f - ww[h] * e4[h].x, 1.0f - ww[h] * e4[h].y, 1.0f - ww[h] * e4[h].z, 1.0f - ww[h] * e4[h].w);
+              E.x *= F[h].x; E.y *= F[h].y; E.z *= F[h].z; E.w *= F[h].w;
+              A.x = fmaf(ww[h], a4[h].x, A.x); A.y = fmaf(ww[h], a4[h].y, A.y);
+              A.z = fmaf(ww[h], a4[h].z, A.z); A.w = fmaf(ww[h], a4[h].w, A.w);
+            }
+            const float4 mn = make_float4(fmaf(m.x, E.x, A.x), fmaf(m.y, E.y, A.y), fmaf(m.z, E.z, A.z), fmaf(m.w, E.w, A.w));
+            const float4 mu = q.write_first ? mn : m;
+            float4 dmu = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float wr = wv[r * Np + n];
+              dmu.x = fmaf(wr, dr4[r].x, dmu.x); dmu.y = fmaf(wr, dr4[r].y, dmu.y);
+              dmu.z = fmaf(wr, dr4[r].z, dmu.z); dmu.w = fmaf(wr, dr4[r].w, dmu.w);
+              v[i * H + r] = dot4(dr4[r], mu);
+            }
+            float4 dt = dmn;                                // dL/dM_t including the read path if write_first
+            if (q.write_first) { dt.x += dmu.x; dt.y += dmu.y; dt.z += dmu.z; dt.w += dmu.w; }
+            const float4 dE = make_float4(dt.x * m.x, dt.y * m.y, dt.z * m.z, dt.w * m.w);
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+              float4 pex = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+              for (int o = 0; o < W; ++o)
+                if (o != h) { pex.x *= F[o].x; pex.y *= F[o].y; pex.z *= F[o].z; pex.w *= F[o].w; }
+              const float4 dF = make_float4(dE.x * pex.x, dE.y * pex.y, dE.z * pex.z, dE.w * pex.w);
+              v[i * H + R + h] = dot4(dt, a4[h]) - dot4(dF, e4[h]);
+              dea[h].x -= dF.x * ww[h]; dea[h].y -= dF.y * ww[h]; dea[h].z -= dF.z * ww[h]; dea[h].w -= dF.w * ww[h];
+              daa[h].x = fmaf(dt.x, ww[h], daa[h].x); daa[h].y = fmaf(dt.y, ww[h], daa[h].y);
+              daa[h].z = fmaf(dt.z, ww[h], daa[h].z); daa[h].w = fmaf(dt.w, ww[h], daa[h].w);
+            }
+            float4 dout = make_float4(dt.x * E.x, dt.y * E.y, dt.z * E.z, dt.w * E.w);
+            if (!q.write_first) { dout.x += dmu.x; dout.y += dmu.y; dout.z += dmu.z; dout.w += dmu.w; }
+            st4(dMb + (size_t)n * M, M, 4 * c, dout);
+          }
         }
-        float4 dt = dmn;                                // dL/dM_t including the read path if write_first
-        if (q.write_first) { dt.x += dmu.x; dt.y += dmu.y; dt.z += dmu.z; dt.w += dmu.w; }
-        const float4 dE = make_float4(dt.x * m.x, dt.y * m.y, dt.z * m.z, dt.w * m.w);
-#pragma unroll
-        for (int h = 0; h < W; ++h) {
-          float4 pex = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-          for (int o = 0; o < W; ++o)
-            if (o != h) { pex.x *= F[o].x; pex.y *= F[o].y; pex.z *= F[o].z; pex.w *= F[o].w; }
-          const float4 dF = make_float4(dE.x * pex.x, dE.y * pex.y, dE.z * pex.z, dE.w * pex.w);
-          part[R + h] = dot4(dt, a4[h]) - dot4(dF, e4[h]);
-          dea[h].x -= dF.x * ww[h]; dea[h].y -= dF.y * ww[h]; dea[h].z -= dF.z * ww[h]; dea[h].w -= dF.w * ww[h];
-          daa[h].x = fmaf(dt.x, ww[h], daa[h].x); daa[h].y = fmaf(dt.y, ww[h], daa[h].y);
-          daa[h].z = fmaf(dt.z, ww[h], daa[h].z); daa[h].w = fmaf(dt.w, ww[h], daa[h].w);
-        }
-        float4 dout = make_float4(dt.x * E.x, dt.y * E.y, dt.z * E.z, dt.w * E.w);
-        if (!q.write_first) { dout.x += dmu.x; dout.y += dmu.y; dout.z += dmu.z; dout.w += dmu.w; }
-        st4(dMb + (size_t)n * M, M, 4 * c, dout);
       }
-#pragma unroll
-      for (int h = 0; h < H; ++h) part[h] = warp_sum(part[h]);
-      if (lane == 0 && rg < q.RG && n < N) {
-#pragma unroll
-        for (int h = 0; h < H; ++h) rowbuf[((size_t)n * q.TW + wrow) * H + h] = part[h];
-      }
+      const float tot = warp_transpose_sum(v, lane);
+      const int vi = lane / H, vh = lane - vi * H;
+      if (lane < 4 * H && rg < q.RG && n0 + vi < N) rowbuf[((size_t)(n0 + vi) * q.TW + wrow) * H + vh] = tot;
     }
     if (cvalid) {
 #pragma unroll
@@ -393,39 +451,45 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
   }
   __syncthreads();
 
-  // ---- (7) B2: column sums dL/dkhat and the column-norm term ----
+  // ---- (7) B2: column sums  A[h][d] = sum_n dsim[h][n] M[n][d]  ->  dL/dkhat = A * cn,  ct = sum_h khat * A ----
   {
-    constexpr int NQ = H + 1;
-    float4 acc[NQ], kh4[H], cn4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[H];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < H; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cvalid) {
-      cn4 = *reinterpret_cast<const float4*>(cn + 4 * c);
+      for (int q0 = rg; q0 < NQ; q0 += q.RG) {
+        const int n0 = 4 * q0;
+        float4 m4[4];
 #pragma unroll
-      for (int h = 0; h < H; ++h) kh4[h] = *reinterpret_cast<const float4*>(khat + h * M4 + 4 * c);
-      for (int n = rg; n < N; n += q.RG) {
-        const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
-        float4 dmh = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) m4[i] = ld4(Mb + (size_t)min(n0 + i, N - 1) * M, M, 4 * c);
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          const float ds = dsim[h * Np + n];
-          dmh.x = fmaf(ds, kh4[h].x, dmh.x); dmh.y = fmaf(ds, kh4[h].y, dmh.y);
-          dmh.z = fmaf(ds, kh4[h].z, dmh.z); dmh.w = fmaf(ds, kh4[h].w, dmh.w);
-          acc[h].x = fmaf(ds, m.x * cn4.x, acc[h].x); acc[h].y = fmaf(ds, m.y * cn4.y, acc[h].y);
-          acc[h].z = fmaf(ds, m.z * cn4.z, acc[h].z); acc[h].w = fmaf(ds, m.w * cn4.w, acc[h].w);
+        for (int i = 0; i < 4; ++i) {
+          if (n0 + i < N) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              const float ds = dsim[h * Np + n0 + i];
+              acc[h].x = fmaf(ds, m4[i].x, acc[h].x); acc[h].y = fmaf(ds, m4[i].y, acc[h].y);
+              acc[h].z = fmaf(ds, m4[i].z, acc[h].z); acc[h].w = fmaf(ds, m4[i].w, acc[h].w);
+            }
+          }
         }
-        acc[H].x = fmaf(dmh.x, m.x, acc[H].x); acc[H].y = fmaf(dmh.y, m.y, acc[H].y);
-        acc[H].z = fmaf(dmh.z, m.z, acc[H].z); acc[H].w = fmaf(dmh.w, m.w, acc[H].w);
       }
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) *reinterpret_cast<float4*>(colbuf + ((size_t)rg * NQ + i) * M4 + 4 * c) = acc[i];
+      for (int i = 0; i < H; ++i) *reinterpret_cast<float4*>(colbuf + ((size_t)rg * H + i) * M4 + 4 * c) = acc[i];
     }
     __syncthreads();
-    for (int i = tid; i < NQ * M4; i += NT) {
-      const int qq = i / M4, d = i - qq * M4;
-      float s = 0.0f;
-      for (int r2 = 0; r2 < q.RG; ++r2) s += colbuf[((size_t)r2 * NQ + qq) * M4 + d];
-      if (qq < H) dkh[qq * M4 + d] = s; else ct[d] = s;
+    for (int d = tid; d < M4; d += NT) {
+      float ctd = 0.0f;
+      const float cnd = cn[d];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float s = 0.0f;
+        for (int r2 = 0; r2 < q.RG; ++r2) s += colbuf[((size_t)r2 * H + h) * M4 + d];
+        const float sc2 = s * cnd;                        // sum_n dsim[h][n] * M[n][d] * cn[d]
+        dkh[h * M4 + d] = sc2;
+        ctd = fmaf(khat[h * M4 + d], sc2, ctd);
+      }
+      ct[d] = ctd;                                        // sum_n (sum_h dsim khat) * M * cn  (the cn factor folded in)
     }
     __syncthreads();
   }
@@ -438,21 +502,35 @@ __global__ void __launch_bounds__(NT, 1) mem_backward_kernel(const BwdParams q) 
     float4 kh4[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) kh4[h] = *reinterpret_cast<const float4*>(khat + h * M4 + 4 * c);
-    const float4 c3 = make_float4(ok4.x * cn4.x * cn4.x * cn4.x * ct4.x, ok4.y * cn4.y * cn4.y * cn4.y * ct4.y,
-                                  ok4.z * cn4.z * cn4.z * cn4.z * ct4.z, ok4.w * cn4.w * cn4.w * cn4.w * ct4.w);
-    for (int n = rg; n < N; n += q.RG) {
-      const float4 m = ld4(Mb + (size_t)n * M, M, 4 * c);
-      float4 d = ld4(dMb + (size_t)n * M, M, 4 * c);
-      float4 dmh = make_float4(0.f, 0.f, 0.f, 0.f);
+    // d(M cn)/dM: cn * dmh - M * cn^3 * sum_n(dmh M); ct already carries one factor cn
+    const float4 c3 = make_float4(ok4.x * cn4.x * cn4.x * ct4.x, ok4.y * cn4.y * cn4.y * ct4.y,
+                                  ok4.z * cn4.z * cn4.z * ct4.z, ok4.w * cn4.w * cn4.w * ct4.w);
+    for (int q0 = rg; q0 < NQ; q0 += q.RG) {
+      const int n0 = 4 * q0;
+      float4 m4[4], d4[4];
 #pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float ds = dsim[h * Np + n];
-        dmh.x = fmaf(ds, kh4[h].x, dmh.x); dmh.y = fmaf(ds, kh4[h].y, dmh.y);
-        dmh.z = fmaf(ds, kh4[h].z, dmh.z); dmh.w = fmaf(ds, kh4[h].w, dmh.w);
+      for (int i = 0; i < 4; ++i) {
+        const int n = min(n0 + i, N - 1);
+        m4[i] = ld4(Mb + (size_t)n * M, M, 4 * c);
+        d4[i] = ld4(dMb + (size_t)n * M, M, 4 * c);
       }
-      d.x += cn4.x * dmh.x - m.x * c3.x; d.y += cn4.y * dmh.y - m.y * c3.y;
-      d.z += cn4.z * dmh.z - m.z * c3.z; d.w += cn4.w * dmh.w - m.w * c3.w;
-      st4(dMb + (size_t)n * M, M, 4 * c, d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + i;
+        if (n < N) {
+          float4 dmh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float ds = dsim[h * Np + n];
+            dmh.x = fmaf(ds, kh4[h].x, dmh.x); dmh.y = fmaf(ds, kh4[h].y, dmh.y);
+            dmh.z = fmaf(ds, kh4[h].z, dmh.z); dmh.w = fmaf(ds, kh4[h].w, dmh.w);
+          }
+          float4 d = d4[i];
+          d.x += cn4.x * dmh.x - m4[i].x * c3.x; d.y += cn4.y * dmh.y - m4[i].y * c3.y;
+          d.z += cn4.z * dmh.z - m4[i].z * c3.z; d.w += cn4.w * dmh.w - m4[i].w * c3.w;
+          st4(dMb + (size_t)n * M, M, 4 * c, d);
+        }
+      }
     }
   }
 
@@ -530,8 +608,9 @@ static BwdKernel select_bwd(int R, int W) {
 int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float* M_prev, const float* w_prev,
                            const float* raw_params, const float* d_read, long long sdr, const float* d_w, float* dM,
                            float* d_w_prev, float* d_raw_params, const float* dlogits, int T, int t,
-                           cudaStream_t stream) {
+                           const float* sim_hist, const float* cn_hist, cudaStream_t stream) {
   BwdParams q{};
+  q.sim_hist = sim_hist; q.cn_hist = cn_hist;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W;
   q.N = s->mem_size; q.M = s->mem_dim; q.M4 = (q.M + 3) / 4 * 4; q.MC = q.M4 / 4; q.Np = (q.N + 3) / 4 * 4;
   q.S = 2 * s->shift_range + 1; q.shift0 = -((q.S + 1) / 2); q.R = R; q.W = W; q.H = H;
@@ -546,13 +625,13 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
   q.dlogits = dlogits; q.T = T; q.t = t; q.O = s->output_dim;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
-  q.oK = take(H * q.M4); q.oKhat = take(H * q.M4); q.oKc = take(H * q.M4); q.oE = take(W * q.M4); q.oA = take(W * q.M4);
+  q.oK = take(H * q.M4); q.oKhat = take(H * q.M4); q.oE = take(W * q.M4); q.oA = take(W * q.M4);
   q.oCn = take(q.M4); q.oCok = take(q.M4); q.oDkh = take(H * q.M4); q.oDe = take(W * q.M4); q.oDa = take(W * q.M4);
   q.oCt = take(q.M4);
   q.oSim = take(H * q.Np); q.oWc = take(H * q.Np); q.oWg = take(H * q.Np); q.oWt = take(H * q.Np); q.oPw = take(H * q.Np);
   q.oW = take(H * q.Np); q.oDw = take(H * q.Np); q.oDsim = take(H * q.Np); q.oWp = take(H * q.Np);
   q.oRow = take(q.N * q.TW * H);
-  q.oCol = take(q.RG * std::max(2 * W, H + 1) * q.M4);
+  q.oCol = take(q.RG * std::max(2 * W, H) * q.M4);
   q.oSc = take(5 * H + 2 * H * SMAX + 4 * H);
   const int smem = 4 * o;
   if (smem > B200_SMEM_OPTIN) return NTM_B200_ERR_TOO_LARGE;
@@ -607,7 +686,7 @@ extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_
   if (!on_sm100()) return NTM_B200_ERR_NO_DEVICE;
   return ntm_b200::train::launch_memory_backward(s, batch, M_prev, w_prev, raw_params, d_read,
                                                  (long long)s->read_head_size * s->mem_dim, d_w, dM, d_w_prev,
-                                                 d_raw_params, nullptr, 1, 0, static_cast<cudaStream_t>(stream));
+                                                 d_raw_params, nullptr, 1, 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, const float* dh_a, const float* dh_b,

@@ -10,11 +10,12 @@ namespace train {
 
 // One reverse-time step of the memory / addressing backward for `batch` sequences (see
 // ntm_b200_memory_backward_step).  d_read: sequences `sdr` floats apart; dlogits (may be null) [B,T,O]
-// fills the logit slots of d_raw for step t.  Returns an ntm_b200_status.
+// fills the logit slots of d_raw for step t; sim_hist [B,H,N] / cn_hist [B,M] (both or neither): what the
+// forward pass recorded for this step (ntm_b200_history::sim / ::cn).  Returns an ntm_b200_status.
 int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float* M_prev, const float* w_prev,
                            const float* raw_params, const float* d_read, long long sdr, const float* d_w, float* dM,
                            float* d_w_prev, float* d_raw_params, const float* dlogits, int T, int t,
-                           cudaStream_t stream);
+                           const float* sim_hist, const float* cn_hist, cudaStream_t stream);
 
 // BasicLSTMCell backward, elementwise part.  dh = dh_a[b*lda + u] (null = 0) + sum over `nslab` K-slice slabs
 // of dh_b[s*slab + b*ldb + u] (null = 0).

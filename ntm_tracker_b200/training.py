@@ -116,6 +116,8 @@ class NTMTrainer(object):
                 "params": self._buffer("params", (T, B, PO4)), "z": self._buffer("z", (T, B, L, 4, Cc)),
                 "c": self._buffer("c", (T + 1, B, L, Cc)), "h": self._buffer("h", (T + 1, B, L, Cc)),
                 "read": self._buffer("read", (T + 1, B, R * M)),
+                # by-products of the forward pass that spare the backward two sweeps over the memory
+                "sim": self._buffer("sim", (T, B, H, N)), "cn": self._buffer("cn", (T, B, M)),
             }
             state = cell.zero_state(B, self.tracker.initializer)     # views of the (re-homed) variables
             logits, _, final_state, _ = cell._run(x, state, T, history=hist)
