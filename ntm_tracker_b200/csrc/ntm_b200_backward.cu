@@ -364,13 +364,14 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
                                        hist->params + (size_t)t * B * PO4, dcat[0], y.ncat[0], dwbuf[cur], dM,
                                        dwbuf[cur ^ 1], draw, dlogits, (int)T, (int)t,
                                        (hist->sim && hist->cn) ? hist->sim + (size_t)t * B * H * N : nullptr,
-                                       (hist->sim && hist->cn) ? hist->cn + (size_t)t * B * M : nullptr, stream);
+                                       (hist->sim && hist->cn) ? hist->cn + (size_t)t * B * M : nullptr, rowDraw, y.pA.KAtot,
+                                       stream);
     if (st) return st == NTM_B200_ERR_CUDA ? set_cuda_error_ext(cudaGetLastError(), "mem_backward_kernel") : st;
     cur ^= 1;
     // d_h(top) = d_raw @ [W_addr | W_out]^T, K slices into slabs
-    BWD_CK(gemmt::pack(draw, PO4, 1, 0, 0, (int)B, PO4, rowDraw, y.pA.KAtot, 0, 0, false, nsm, stream), "pack(d_raw)");
+    // (the memory-backward kernel has already written d_raw into the row-operand tiles)
     BWD_CK(gemmt::launch(y.pA, rowDraw, colWao, dh, C, B * (long long)C, stream), "gemm_tiles(d_h)");
-    count_launch(); count_launch();
+    count_launch();
     for (int l = L - 1; l >= 0; --l) {
       const float* dh_b = (l == L - 1) ? dh : dcat[l + 1];
       const long long ldb = (l == L - 1) ? C : y.ncat[l + 1];
@@ -379,13 +380,17 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
       st = train::launch_lstm_backward(B, C, dcat[l] + (y.ncat[l] - C), y.ncat[l], dh_b, ldb, nslab, B * (long long)C,
                                        hist->z + ((size_t)t * B * L + l) * 4 * C, (long long)L * 4 * C,
                                        hist->c + ((size_t)t * B * L + l) * C, hist->c + ((size_t)(t + 1) * B * L + l) * C,
-                                       (long long)L * C, dc + (size_t)l * B * C, dz, (long long)L * 4 * C, stream);
+                                       (long long)L * C, dc + (size_t)l * B * C, dz, (long long)L * 4 * C, rowDz, y.pB[l].KAtot,
+                                       stream);
       if (st) return set_cuda_error_ext(cudaGetLastError(), "lstm_backward_kernel");
       // d_cat_l = d_z_l @ W_l[off:]^T  -> [d_read | d_h_l] (layer 0) or [d_h_{l-1} (this step) | d_h_l (previous step)]
-      BWD_CK(gemmt::pack(dz, (long long)L * 4 * C, 1, 0, 0, (int)B, 4 * C, rowDz, y.pB[l].KAtot, 0, 0, false, nsm, stream), "pack(d_z)");
+      if (C % 8 != 0) {     // (else the LSTM backward kernel has written d_z into the row-operand tiles itself)
+        BWD_CK(gemmt::pack(dz, (long long)L * 4 * C, 1, 0, 0, (int)B, 4 * C, rowDz, y.pB[l].KAtot, 0, 0, false, nsm, stream), "pack(d_z)");
+        count_launch();
+      }
       BWD_CK(gemmt::launch(y.pB[l], rowDz, reinterpret_cast<uint8_t*>(ws + y.off_colWl[l]), dcat[l], y.ncat[l], 0, stream),
              "gemm_tiles(d_cat)");
-      count_launch(); count_launch();
+      count_launch();
     }
   }
   float* dw_final = dwbuf[cur];          // gradient w.r.t. the weightings entering step 0

@@ -23,6 +23,7 @@
 #include "ntm_b200.h"
 #include "ntm_b200_params.h"
 #include "ntm_b200_train.h"
+#include "ntm_b200_gemm_ws.cuh"
 
 namespace ntm_b200 {
 namespace train {
@@ -35,6 +36,8 @@ struct BwdParams {
   int TPR, RG, TW;            // threads per row (multiple of 32), row groups, warps per row
   const float* sim_hist;      // [B, H, N] un-normalised similarities the forward pass recorded, or null
   const float* cn_hist;       // [B, M] inverse column norms the forward pass recorded, or null
+  uint8_t* tiles_raw;         // operand tiles receiving d_raw (row operand of the d_h GEMM), or null
+  int KAtot_raw;
   const float* M_prev;        // [B, N, M]
   const float* w_prev;        // [B, H, N]
   const float* raw;           // [B, PO4]
@@ -67,6 +70,19 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
+// VEC: M % 4 == 0 and every row base 16-byte aligned (checked once on the host): plain vector accesses
+template <bool VEC>
+__device__ __forceinline__ float4 ld4t(const float* base, int M, int d0);
+template <>
+__device__ __forceinline__ float4 ld4t<true>(const float* base, int, int d0) {
+  return __ldcg(reinterpret_cast<const float4*>(base + d0));
+}
+template <bool VEC>
+__device__ __forceinline__ void st4t(float* base, int M, int d0, const float4& v);
+template <>
+__device__ __forceinline__ void st4t<true>(float* base, int, int d0, const float4& v) {
+  __stcg(reinterpret_cast<float4*>(base + d0), v);
+}
 __device__ __forceinline__ float4 ld4(const float* base, int M, int d0) {
   // row pointer `base`, columns d0..d0+3 of a row of M valid floats (vector load when aligned)
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -84,6 +100,11 @@ __device__ __forceinline__ void st4(float* base, int M, int d0, const float4& v)
   if (d0 + 2 < M) base[d0 + 2] = v.z;
   if (d0 + 3 < M) base[d0 + 3] = v.w;
 }
+
+template <>
+__device__ __forceinline__ float4 ld4t<false>(const float* base, int M, int d0) { return ld4(base, M, d0); }
+template <>
+__device__ __forceinline__ void st4t<false>(float* base, int M, int d0, const float4& v) { st4(base, M, d0, v); }
 
 // Transposing warp reduction of NV <= 32 per-lane partial sums: at offset o a lane keeps one half of its value
 // list and receives the partner's sums of that half; lane L ends with the warp total of value L (fixed order).
@@ -106,7 +127,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // consecutive chunks of one row group (TW = TPR / 32 warps per row).  Every sweep over the memory handles a
 // QUAD of four consecutive rows per iteration (four independent loads in flight; 4 * H <= 28 row partials per
 // lane, combined by one transposing reduction per quad).  Two CTAs per SM.
-template <int R, int W>
+template <int R, int W, bool VEC>
 __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) {
   constexpr int H = R + W;
   extern __shared__ __align__(16) float sm[];
@@ -226,7 +247,7 @@ __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) 
       if (cvalid && n0 < N) {
         float4 m[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m[i] = ld4(Mb + (size_t)min(n0 + i, N - 1) * M, M, 4 * c);
+        for (int i = 0; i < 4; ++i) m[i] = ld4t<VEC>(Mb + (size_t)min(n0 + i, N - 1) * M, M, 4 * c);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -294,65 +315,78 @@ __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) 
       dea[h] = make_float4(0.f, 0.f, 0.f, 0.f);
       daa[h] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // Software pipeline over PAIRS of rows: while a pair is being worked on, the loads of the next pair
+    // (second half of the quad, then the first half of the next quad) are already in flight.
+    float v[32];
+    auto load_pair = [&](int n0p, float4 (&m)[2], float4 (&d)[2]) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const size_t ro = (size_t)min(n0p + i, N - 1) * M;
+        m[i] = ld4t<VEC>(Mb + ro, M, 4 * c);
+        d[i] = ld4t<VEC>(dMb + ro, M, 4 * c);
+      }
+    };
+    auto compute_pair = [&](int n0p, const float4 (&m2)[2], const float4 (&d2)[2], int vbase) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = n0p + i;
+        if (n < N) {
+          const float4 m = m2[i], dmn = d2[i];
+          float ww[W];
+          float4 F[W];
+          float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int h = 0; h < W; ++h) {
+            ww[h] = wv[(R + h) * Np + n];
+            F[h] = make_float4(1.0f - ww[h] * e4[h].x, 1.0f - ww[h] * e4[h].y, 1.0f - ww[h] * e4[h].z, 1.0f - ww[h] * e4[h].w);
+            E.x *= F[h].x; E.y *= F[h].y; E.z *= F[h].z; E.w *= F[h].w;
+            A.x = fmaf(ww[h], a4[h].x, A.x); A.y = fmaf(ww[h], a4[h].y, A.y);
+            A.z = fmaf(ww[h], a4[h].z, A.z); A.w = fmaf(ww[h], a4[h].w, A.w);
+          }
+          const float4 mn = make_float4(fmaf(m.x, E.x, A.x), fmaf(m.y, E.y, A.y), fmaf(m.z, E.z, A.z), fmaf(m.w, E.w, A.w));
+          const float4 mu = q.write_first ? mn : m;
+          float4 dmu = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float wr = wv[r * Np + n];
+            dmu.x = fmaf(wr, dr4[r].x, dmu.x); dmu.y = fmaf(wr, dr4[r].y, dmu.y);
+            dmu.z = fmaf(wr, dr4[r].z, dmu.z); dmu.w = fmaf(wr, dr4[r].w, dmu.w);
+            v[vbase + i * H + r] = dot4(dr4[r], mu);
+          }
+          float4 dt = dmn;                                // dL/dM_t including the read path if write_first
+          if (q.write_first) { dt.x += dmu.x; dt.y += dmu.y; dt.z += dmu.z; dt.w += dmu.w; }
+          const float4 dE = make_float4(dt.x * m.x, dt.y * m.y, dt.z * m.z, dt.w * m.w);
+#pragma unroll
+          for (int h = 0; h < W; ++h) {
+            float4 pex = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+            for (int o = 0; o < W; ++o)
+              if (o != h) { pex.x *= F[o].x; pex.y *= F[o].y; pex.z *= F[o].z; pex.w *= F[o].w; }
+            const float4 dF = make_float4(dE.x * pex.x, dE.y * pex.y, dE.z * pex.z, dE.w * pex.w);
+            v[vbase + i * H + R + h] = dot4(dt, a4[h]) - dot4(dF, e4[h]);
+            dea[h].x -= dF.x * ww[h]; dea[h].y -= dF.y * ww[h]; dea[h].z -= dF.z * ww[h]; dea[h].w -= dF.w * ww[h];
+            daa[h].x = fmaf(dt.x, ww[h], daa[h].x); daa[h].y = fmaf(dt.y, ww[h], daa[h].y);
+            daa[h].z = fmaf(dt.z, ww[h], daa[h].z); daa[h].w = fmaf(dt.w, ww[h], daa[h].w);
+          }
+          float4 dout = make_float4(dt.x * E.x, dt.y * E.y, dt.z * E.z, dt.w * E.w);
+          if (!q.write_first) { dout.x += dmu.x; dout.y += dmu.y; dout.z += dmu.z; dout.w += dmu.w; }
+          st4t<VEC>(dMb + (size_t)n * M, M, 4 * c, dout);
+        }
+      }
+    };
+    float4 mA[2], dA[2], mB[2], dB[2];
+    if (cvalid && 4 * rg < N) load_pair(4 * rg, mA, dA);
     for (int q0 = 0; q0 < NQ; q0 += q.RG) {
       const int n0 = 4 * (q0 + rg);
-      float v[32];
+      const bool active = cvalid && n0 < N;
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-      if (cvalid && n0 < N) {
-        float4 m4[4], dm4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = min(n0 + i, N - 1);
-          m4[i] = ld4(Mb + (size_t)n * M, M, 4 * c);
-          dm4[i] = ld4(dMb + (size_t)n * M, M, 4 * c);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = n0 + i;
-          if (n < N) {
-            const float4 m = m4[i], dmn = dm4[i];
-            float ww[W];
-            float4 F[W];
-            float4 E = make_float4(1.f, 1.f, 1.f, 1.f), A = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int h = 0; h < W; ++h) {
-              ww[h] = wv[(R + h) * Np + n];
-              F[h] = make_float4(1.0f - ww[h] * e4[h].x, 1.0f - ww[h] * e4[h].y, 1.0f - ww[h] * e4[h].z, 1.0f - ww[h] * e4[h].w);
-              E.x *= F[h].x; E.y *= F[h].y; E.z *= F[h].z; E.w *= F[h].w;
-              A.x = fmaf(ww[h], a4[h].x, A.x); A.y = fmaf(ww[h], a4[h].y, A.y);
-              A.z = fmaf(ww[h], a4[h].z, A.z); A.w = fmaf(ww[h], a4[h].w, A.w);
-            }
-            const float4 mn = make_float4(fmaf(m.x, E.x, A.x), fmaf(m.y, E.y, A.y), fmaf(m.z, E.z, A.z), fmaf(m.w, E.w, A.w));
-            const float4 mu = q.write_first ? mn : m;
-            float4 dmu = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const float wr = wv[r * Np + n];
-              dmu.x = fmaf(wr, dr4[r].x, dmu.x); dmu.y = fmaf(wr, dr4[r].y, dmu.y);
-              dmu.z = fmaf(wr, dr4[r].z, dmu.z); dmu.w = fmaf(wr, dr4[r].w, dmu.w);
-              v[i * H + r] = dot4(dr4[r], mu);
-            }
-            float4 dt = dmn;                                // dL/dM_t including the read path if write_first
-            if (q.write_first) { dt.x += dmu.x; dt.y += dmu.y; dt.z += dmu.z; dt.w += dmu.w; }
-            const float4 dE = make_float4(dt.x * m.x, dt.y * m.y, dt.z * m.z, dt.w * m.w);
-#pragma unroll
-            for (int h = 0; h < W; ++h) {
-              float4 pex = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-              for (int o = 0; o < W; ++o)
-                if (o != h) { pex.x *= F[o].x; pex.y *= F[o].y; pex.z *= F[o].z; pex.w *= F[o].w; }
-              const float4 dF = make_float4(dE.x * pex.x, dE.y * pex.y, dE.z * pex.z, dE.w * pex.w);
-              v[i * H + R + h] = dot4(dt, a4[h]) - dot4(dF, e4[h]);
-              dea[h].x -= dF.x * ww[h]; dea[h].y -= dF.y * ww[h]; dea[h].z -= dF.z * ww[h]; dea[h].w -= dF.w * ww[h];
-              daa[h].x = fmaf(dt.x, ww[h], daa[h].x); daa[h].y = fmaf(dt.y, ww[h], daa[h].y);
-              daa[h].z = fmaf(dt.z, ww[h], daa[h].z); daa[h].w = fmaf(dt.w, ww[h], daa[h].w);
-            }
-            float4 dout = make_float4(dt.x * E.x, dt.y * E.y, dt.z * E.z, dt.w * E.w);
-            if (!q.write_first) { dout.x += dmu.x; dout.y += dmu.y; dout.z += dmu.z; dout.w += dmu.w; }
-            st4(dMb + (size_t)n * M, M, 4 * c, dout);
-          }
-        }
+      if (active) {
+        load_pair(n0 + 2, mB, dB);
+        compute_pair(n0, mA, dA, 0);
+        const int nn0 = n0 + 4 * q.RG;
+        if (nn0 < N) load_pair(nn0, mA, dA);
+        compute_pair(n0 + 2, mB, dB, 2 * H);
       }
       const float tot = warp_transpose_sum(v, lane);
       const int vi = lane / H, vh = lane - vi * H;
@@ -461,7 +495,7 @@ __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) 
         const int n0 = 4 * q0;
         float4 m4[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m4[i] = ld4(Mb + (size_t)min(n0 + i, N - 1) * M, M, 4 * c);
+        for (int i = 0; i < 4; ++i) m4[i] = ld4t<VEC>(Mb + (size_t)min(n0 + i, N - 1) * M, M, 4 * c);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (n0 + i < N) {
@@ -511,8 +545,8 @@ __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int n = min(n0 + i, N - 1);
-        m4[i] = ld4(Mb + (size_t)n * M, M, 4 * c);
-        d4[i] = ld4(dMb + (size_t)n * M, M, 4 * c);
+        m4[i] = ld4t<VEC>(Mb + (size_t)n * M, M, 4 * c);
+        d4[i] = ld4t<VEC>(dMb + (size_t)n * M, M, 4 * c);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -528,7 +562,7 @@ __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) 
           float4 d = d4[i];
           d.x += cn4.x * dmh.x - m4[i].x * c3.x; d.y += cn4.y * dmh.y - m4[i].y * c3.y;
           d.z += cn4.z * dmh.z - m4[i].z * c3.z; d.w += cn4.w * dmh.w - m4[i].w * c3.w;
-          st4(dMb + (size_t)n * M, M, 4 * c, d);
+          st4t<VEC>(dMb + (size_t)n * M, M, 4 * c, d);
         }
       }
     }
@@ -564,53 +598,82 @@ __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) 
     const int o = i - q.P;
     draw[i] = (q.dlogits != nullptr && o < q.O) ? q.dlogits[((size_t)b * q.T + q.t) * q.O + o] : 0.0f;
   }
+  if (q.tiles_raw != nullptr) {
+    // the row operand of d_h = d_raw @ [W_addr | W_out]^T: this sequence's d_raw row as bf16 hi/lo tile records
+    // (the CTA re-reads the row it has just written; 8 consecutive entries per 16-byte chunk)
+    __syncthreads();
+    for (int ch = tid; 8 * ch < q.PO4; ch += NT) {
+      float v8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v8[e] = (8 * ch + e < q.PO4) ? draw[8 * ch + e] : 0.0f;
+      gemmws::store_split8(q.tiles_raw, q.KAtot_raw, b, 8 * ch, v8);
+    }
+  }
 }
 
 // LSTM cell backward for one layer and one timestep, all sequences: elementwise over [B, C].
 // BasicLSTMCell forward (TF 1.0/1.1): c' = c*sig(f) + sig(i)*tanh(j); h' = tanh(c')*sig(o).
-__global__ void lstm_backward_kernel(int B, int C, const float* __restrict__ dh_a, long long lda,
+__global__ void __launch_bounds__(256) lstm_backward_kernel(int B, int C, const float* __restrict__ dh_a, long long lda,
                                      const float* __restrict__ dh_b, long long ldb, int nslab, long long slab,
                                      const float* __restrict__ z, long long z_stride,
                                      const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                      long long c_stride, float* __restrict__ dc, float* __restrict__ dz,
-                                     long long dz_stride) {
-  const int total = B * C;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int b = i / C, u = i - b * C;
-    const float* zb = z + (size_t)b * z_stride;
-    const float gi = sigmoid_f(zb[u]), gj = tanhf(zb[C + u]), gf = sigmoid_f(zb[2 * C + u]), go = sigmoid_f(zb[3 * C + u]);
-    const float cp = c_prev[(size_t)b * c_stride + u], tc = tanhf(c_new[(size_t)b * c_stride + u]);
-    float dh = dh_a != nullptr ? dh_a[(size_t)b * lda + u] : 0.0f;
-    if (dh_b != nullptr)
-      for (int s2 = 0; s2 < nslab; ++s2) dh += dh_b[(size_t)s2 * slab + (size_t)b * ldb + u];   // K-slice slabs, slice order
-    const float dct = dc[i] + dh * go * (1.0f - tc * tc);
+                                     long long dz_stride, uint8_t* tiles, int KAtot) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i0 < (long long)B * C;
+  const long long i = live ? i0 : 0;            // tail lanes recompute element 0 and store nothing
+  const int b = (int)(i / C), u = (int)(i - (long long)b * C);
+  const float* zb = z + (size_t)b * z_stride;
+  const float gi = sigmoid_f(zb[u]), gj = tanhf(zb[C + u]), gf = sigmoid_f(zb[2 * C + u]), go = sigmoid_f(zb[3 * C + u]);
+  const float cp = c_prev[(size_t)b * c_stride + u], tc = tanhf(c_new[(size_t)b * c_stride + u]);
+  float dh = dh_a != nullptr ? dh_a[(size_t)b * lda + u] : 0.0f;
+  if (dh_b != nullptr)
+    for (int s2 = 0; s2 < nslab; ++s2) dh += dh_b[(size_t)s2 * slab + (size_t)b * ldb + u];   // K-slice slabs, slice order
+  const float dct = dc[i] + dh * go * (1.0f - tc * tc);
+  float g4[4];
+  g4[0] = dct * gj * gi * (1.0f - gi);
+  g4[1] = dct * gi * (1.0f - gj * gj);
+  g4[2] = dct * cp * gf * (1.0f - gf);
+  g4[3] = dh * tc * go * (1.0f - go);
+  if (live) {
     float* dzb = dz + (size_t)b * dz_stride;
-    dzb[u] = dct * gj * gi * (1.0f - gi);
-    dzb[C + u] = dct * gi * (1.0f - gj * gj);
-    dzb[2 * C + u] = dct * cp * gf * (1.0f - gf);
-    dzb[3 * C + u] = dh * tc * go * (1.0f - go);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dzb[g * C + u] = g4[g];
     dc[i] = dct * gf;
+  }
+  if (tiles != nullptr) {
+    // row operand of d_cat = d_z @ W^T as bf16 hi/lo tile records (C % 8 == 0: aligned groups of 8 lanes hold 8
+    // consecutive units of one sequence; lane g of a group stores gate g's chunk, k = g * C + u)
+    const int lane = threadIdx.x & 31, l0 = lane & ~7;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v8[e] = __shfl_sync(0xffffffffu, g4[g], l0 + e);
+      if (live && (lane & 7) == g) gemmws::store_split8(tiles, KAtot, b, g * C + (u - g), v8);
+    }
   }
 }
 
 typedef void (*BwdKernel)(const BwdParams);
-#define NTM_BK(R, W) mem_backward_kernel<R, W>
-static BwdKernel select_bwd(int R, int W) {
-  static const BwdKernel table[NTM_B200_MAX_READ_HEADS][NTM_B200_MAX_WRITE_HEADS] = {
+#define NTM_BK(R, W) {mem_backward_kernel<R, W, false>, mem_backward_kernel<R, W, true>}
+static BwdKernel select_bwd(int R, int W, bool vec) {
+  static const BwdKernel table[NTM_B200_MAX_READ_HEADS][NTM_B200_MAX_WRITE_HEADS][2] = {
       {NTM_BK(1, 1), NTM_BK(1, 2), NTM_BK(1, 3)},
       {NTM_BK(2, 1), NTM_BK(2, 2), NTM_BK(2, 3)},
       {NTM_BK(3, 1), NTM_BK(3, 2), NTM_BK(3, 3)},
       {NTM_BK(4, 1), NTM_BK(4, 2), NTM_BK(4, 3)}};
-  return table[R - 1][W - 1];
+  return table[R - 1][W - 1][vec ? 1 : 0];
 }
 
 
 int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float* M_prev, const float* w_prev,
                            const float* raw_params, const float* d_read, long long sdr, const float* d_w, float* dM,
                            float* d_w_prev, float* d_raw_params, const float* dlogits, int T, int t,
-                           const float* sim_hist, const float* cn_hist, cudaStream_t stream) {
+                           const float* sim_hist, const float* cn_hist, uint8_t* tiles_raw, int KAtot_raw,
+                           cudaStream_t stream) {
   BwdParams q{};
-  q.sim_hist = sim_hist; q.cn_hist = cn_hist;
+  q.sim_hist = sim_hist; q.cn_hist = cn_hist; q.tiles_raw = tiles_raw; q.KAtot_raw = KAtot_raw;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W;
   q.N = s->mem_size; q.M = s->mem_dim; q.M4 = (q.M + 3) / 4 * 4; q.MC = q.M4 / 4; q.Np = (q.N + 3) / 4 * 4;
   q.S = 2 * s->shift_range + 1; q.shift0 = -((q.S + 1) / 2); q.R = R; q.W = W; q.H = H;
@@ -635,7 +698,9 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
   q.oSc = take(5 * H + 2 * H * SMAX + 4 * H);
   const int smem = 4 * o;
   if (smem > B200_SMEM_OPTIN) return NTM_B200_ERR_TOO_LARGE;
-  BwdKernel k = select_bwd(R, W);
+  const bool vec = (q.M % 4 == 0) && (sdr % 4 == 0) && ((reinterpret_cast<uintptr_t>(M_prev) | reinterpret_cast<uintptr_t>(dM) |
+                                                         reinterpret_cast<uintptr_t>(d_read)) & 15) == 0;
+  BwdKernel k = select_bwd(R, W, vec);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     cudaGetLastError();
     return NTM_B200_ERR_CUDA;
@@ -648,11 +713,12 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
 int launch_lstm_backward(long long batch, int hidden, const float* dh_a, long long lda, const float* dh_b, long long ldb,
                          int nslab, long long slab, const float* z, long long z_stride, const float* c_prev,
                          const float* c_new, long long c_stride, float* dc, float* dz, long long dz_stride,
-                         cudaStream_t stream) {
-  const int total = (int)(batch * hidden);
-  const int blocks = std::min((total + 255) / 256, B200_SMS * 8);
+                         uint8_t* tiles, int KAtot, cudaStream_t stream) {
+  const long long total = batch * hidden;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (hidden % 8 != 0) tiles = nullptr;      // the caller packs d_z with the generic kernel instead
   lstm_backward_kernel<<<blocks, 256, 0, stream>>>((int)batch, hidden, dh_a, lda, dh_b, ldb, nslab, slab, z, z_stride,
-                                                  c_prev, c_new, c_stride, dc, dz, dz_stride);
+                                                  c_prev, c_new, c_stride, dc, dz, dz_stride, tiles, KAtot);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
 }
@@ -686,7 +752,7 @@ extern "C" int32_t ntm_b200_memory_backward_step(const ntm_b200_shape* s, int64_
   if (!on_sm100()) return NTM_B200_ERR_NO_DEVICE;
   return ntm_b200::train::launch_memory_backward(s, batch, M_prev, w_prev, raw_params, d_read,
                                                  (long long)s->read_head_size * s->mem_dim, d_w, dM, d_w_prev,
-                                                 d_raw_params, nullptr, 1, 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+                                                 d_raw_params, nullptr, 1, 0, nullptr, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, const float* dh_a, const float* dh_b,
@@ -697,5 +763,5 @@ extern "C" int32_t ntm_b200_lstm_backward_step(int64_t batch, int32_t hidden, co
   if (batch < 1 || hidden < 1 || batch * (int64_t)hidden > (1ll << 30)) return NTM_B200_ERR_BAD_SHAPE;
   if (!on_sm100()) return NTM_B200_ERR_NO_DEVICE;
   return ntm_b200::train::launch_lstm_backward(batch, hidden, dh_a, hidden, dh_b, hidden, 1, 0, z, z_stride, c_prev, c_new,
-                                               c_stride, dc, dz, dz_stride, static_cast<cudaStream_t>(stream));
+                                               c_stride, dc, dz, dz_stride, nullptr, 0, static_cast<cudaStream_t>(stream));
 }
