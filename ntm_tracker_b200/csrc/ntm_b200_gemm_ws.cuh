@@ -17,7 +17,8 @@
 //   warp 0      producer: one 32 KiB cp.async.bulk per (row block, K atom) into a ring of 3 slots (7 when the
 //               K slice is <= 256 wide: then the weight lo half lives in TMEM as well and shared memory is all ring)
 //   warp 1      tcgen05.mma issuer (one elected lane); commits release ring slots / publish accumulators
-//   warps 2..5  epilogue: TMEM -> registers -> global, double-buffered against the next row block's MMAs
+//   warps 2..9  epilogue: TMEM -> registers -> global, double-buffered against the next row block's MMAs (two warps
+//               per TMEM lane quarter, 64 accumulator columns each)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -32,7 +33,7 @@ namespace gemmws {
 constexpr int KA_MAX = 8;            // K atoms (64 wide) per slice: 256 TMEM columns of weight hi halves
 constexpr int NSLOT_MAX = 7;         // activation ring slots (32 KiB each): 3 next to a resident weight lo half in
                                      // shared memory, 7 when both weight halves fit TMEM (K slice <= 256)
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int ATOM_BYTES = 16384;    // [128 rows][128 B]
 constexpr int REC_BYTES = 2 * ATOM_BYTES;
 
@@ -46,6 +47,7 @@ struct Args {
   int ldo, ncols, ntiles, kslices, ngroups, KAtot, KA;
   int nslot;             // ring slots
   int wlo_tmem;          // 1: weight lo half in TMEM too (KA <= 4; `wlo` then holds packed words like `whi`)
+  int exp;               // experiment switches (EnvSwitches::exp)
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -77,9 +79,9 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(&wbar, 1);
-    mbar_init(&whibar, 4);
+    mbar_init(&whibar, 8);
     fence_proxy_async_smem();
   }
   tcgen05_fence_before();
@@ -93,18 +95,25 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
 
   if (warp == 0) {
     // ------------------------------------------------ producer ------------------------------------
-    if (lane == 0) {
-      if (!a.wlo_tmem) {
-        mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
-        for (int k = 0; k < nka; ++k)
-          bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
-      }
+    if (lane == 0 && !a.wlo_tmem) {
+      mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
+      for (int k = 0; k < nka; ++k)
+        bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
+    }
+    // Two issuing lanes: lane 0 brings the hi half of a record, lane 1 the lo half (a bulk copy costs its
+    // issuing thread ~240 ns and one thread sustains ~64 GB/s; two copies in flight per slot halve the time a
+    // slot spends filling).  Lane 0 alone arms the barrier with the whole record's byte count: the phase cannot
+    // complete before that arrive, whatever the order in which the two copies land.
+    const int nissue = (a.exp & 1) ? 1 : 2;
+    if (lane < nissue) {
       uint32_t slot = 0, phase = 0;      // ring position kept incrementally (no division on this thread's path)
+      const uint32_t bytes = nissue == 2 ? ATOM_BYTES : REC_BYTES;
+      const size_t half = nissue == 2 ? (size_t)lane * ATOM_BYTES : 0;
       for (long long rb = group; rb < nrb; rb += a.ngroups) {
         for (int k = 0; k < nka; ++k) {
           mbar_wait(&empty[slot], phase ^ 1u);                     // passes on a fresh barrier
-          mbar_expect_tx(&full[slot], REC_BYTES);
-          bulk_g2s(sRing + (size_t)slot * REC_BYTES, a.act + ((size_t)rb * a.KAtot + ka0 + k) * REC_BYTES, REC_BYTES,
+          if (lane == 0) mbar_expect_tx(&full[slot], REC_BYTES);
+          bulk_g2s(sRing + (size_t)slot * REC_BYTES + half, a.act + ((size_t)rb * a.KAtot + ka0 + k) * REC_BYTES + half, bytes,
                    &full[slot]);
           if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
         }
@@ -148,27 +157,37 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
   } else {
     // ------------------------------------------------ epilogue warps ------------------------------
     const int qd = warp & 3;                            // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;                  // two warps share a quarter: accumulator columns [64*chalf, +64)
     const uint32_t lane_addr = (uint32_t)(32 * qd) << 16;
     const int jl = 32 * qd + lane;                      // weight column within the tile = TMEM lane
     const int jcol = tile * 128 + jl;
     // weight hi half -> TMEM (once)
     {
-      const uint32_t* src = a.whi + (wrec * 128 + jl) * (size_t)(a.KA * 32);
-      for (int q = 0; q < nka * 4; ++q) {               // 16 k = 8 packed words per step
-        const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(src + q * 8));
-        const uint4 hi4 = __ldg(reinterpret_cast<const uint4*>(src + q * 8 + 4));
-        const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-        tmem_st_x8(tWhi + lane_addr + q * 8, v);
-      }
-      if (a.wlo_tmem) {
-        const uint32_t* srl = reinterpret_cast<const uint32_t*>(a.wlo) + (wrec * 128 + jl) * (size_t)(a.KA * 32);
-        for (int q = 0; q < nka * 4; ++q) {
-          const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(srl + q * 8));
-          const uint4 hi4 = __ldg(reinterpret_cast<const uint4*>(srl + q * 8 + 4));
-          const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-          tmem_st_x8(tWlo + lane_addr + q * 8, v);
+      // 16 k = 8 packed words per step; four steps' loads are issued together (the staging is a chain of L2
+      // round trips otherwise, and at small batches it is most of the kernel)
+      auto stage_weights = [&](const uint32_t* src, uint32_t tdst) {
+        const int nq = nka * 4;
+        for (int q0 = 4 * chalf; q0 < nq; q0 += 8) {    // the quarter's two warps alternate blocks of four steps
+          uint4 w4[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int q = min(q0 + i, nq - 1);
+            w4[2 * i] = __ldg(reinterpret_cast<const uint4*>(src + q * 8));
+            w4[2 * i + 1] = __ldg(reinterpret_cast<const uint4*>(src + q * 8 + 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (q0 + i < nq) {
+              const uint32_t v[8] = {w4[2 * i].x, w4[2 * i].y, w4[2 * i].z, w4[2 * i].w,
+                                     w4[2 * i + 1].x, w4[2 * i + 1].y, w4[2 * i + 1].z, w4[2 * i + 1].w};
+              tmem_st_x8(tdst + (q0 + i) * 8, v);
+            }
+          }
         }
-      }
+      };
+      stage_weights(a.whi + (wrec * 128 + jl) * (size_t)(a.KA * 32), tWhi + lane_addr);
+      if (a.wlo_tmem)
+        stage_weights(reinterpret_cast<const uint32_t*>(a.wlo) + (wrec * 128 + jl) * (size_t)(a.KA * 32), tWlo + lane_addr);
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
@@ -187,7 +206,7 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
         // short K (few MMAs per row block): the epilogue is on the critical path, and a tcgen05.ld queues
         // behind the MMAs of the next row block -- two 32-column loads in flight per wait (38.5 vs 42 us at C3)
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 64) {
+        for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 64) {
           uint32_t v0[32], v1[32];
           tmem_ld_x32(tAcc + c0, v0);
           tmem_ld_x32(tAcc + c0 + 32, v1);
@@ -209,7 +228,7 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
         // long K: the epilogue hides behind the next row block's MMAs; narrow loads disturb their
         // A-from-TMEM operand reads least (57 vs 64 us at C3 with the wide ones)
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
+        for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 16) {
           uint32_t v[16];
           tmem_ld_x16(tAcc + c0, v);
           tmem_wait_ld();
@@ -342,11 +361,11 @@ inline bool plan_ok(const Plan& p, int nsm) { return p.ntiles * p.kslices <= nsm
 inline int smem_bytes(const Plan& p) { return 1024 + (p.wlo_tmem ? 0 : p.KA * ATOM_BYTES) + p.nslot * REC_BYTES; }
 
 static inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi, const uint8_t* wlo, const float* bias,
-                          float* out, int ldo, long long slab, long long rows, cudaStream_t stream) {
+                          float* out, int ldo, long long slab, long long rows, cudaStream_t stream, int exp = 0) {
   Args a{};
   a.act = act; a.whi = whi; a.wlo = wlo; a.bias = bias; a.out = out; a.rows = rows; a.slab = slab; a.ldo = ldo;
   a.ncols = p.ncols; a.ntiles = p.ntiles; a.kslices = p.kslices; a.ngroups = p.ngroups; a.KAtot = p.KAtot; a.KA = p.KA;
-  a.nslot = p.nslot; a.wlo_tmem = p.wlo_tmem;
+  a.nslot = p.nslot; a.wlo_tmem = p.wlo_tmem; a.exp = exp;
   const int smem = smem_bytes(p);
   static int configured[MAX_DEVICES] = {0};     // cudaFuncSetAttribute is per device
   {

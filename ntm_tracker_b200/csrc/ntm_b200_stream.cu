@@ -1492,7 +1492,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       for (int l = 0; l < L; ++l) {
         const float* wl = w->lstm_w[l] + (l == 0 ? (size_t)s->input_dim * 4 * C : 0);
         if (ws_ok) {
-          e = gemmws::launch(planA, tilesA, whiA, wloA, nullptr, partA, 4 * C, ws.slabA, B, stream);
+          e = gemmws::launch(planA, tilesA, whiA, wloA, nullptr, partA, 4 * C, ws.slabA, B, stream, env.exp);
           count_launch();
           if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(controller)");
         } else {
@@ -1520,7 +1520,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       // ---- head parameters + logits: one GEMM, bias folded in ----
       float* mc_t = hP ? hist->params + (size_t)t * B * PO4 : mcbuf;
       if (ws_ok) {
-        e = gemmws::launch(planC, tilesC, whiC, wloC, bC, mc_t, PO4, 0, B, stream);
+        e = gemmws::launch(planC, tilesC, whiC, wloC, bC, mc_t, PO4, 0, B, stream, env.exp);
         count_launch();
         if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(head parameters)");
       } else {
