@@ -327,6 +327,12 @@ int32_t ntm_b200_last_stream_ms(float* out4, int32_t* steps);
  * drain, finalize, whole CTA}; out12[8] = first CTA start to last CTA end; out12[9..11] = SM cycles warp 0
  * spent in pass 1 {waiting for ring stages, computing, team barrier + bulk-copy issue}.  Synchronous. */
 int32_t ntm_b200_stream_phase_ns(double* out12, int32_t* ctas);
+/* Training (ntm_b200_backward_seq), profiling enabled, stream synchronised: device ms of this thread's last
+ * backward call, out4 = {memory/addressing backward kernel summed over the steps, rest of the reverse-time
+ * loop (data-gradient GEMMs + LSTM gate backward), weight-gradient GEMMs + init_state sums, whole call};
+ * *steps = number of timesteps (0 = nothing recorded).  Measurement hook for bench.py's training roofline
+ * (reference counterpart: none -- tf.gradients has no per-op timing, direct_offset_output.py:611-613). */
+int32_t ntm_b200_last_backward_ms(float* out4, int32_t* steps);
 /* With profiling enabled the persistent kernel also accumulates, per CTA, SM-clock
  * cycles spent in each phase of the timestep (16 int64 slots per CTA: 0/2/4/6 =
  * phases A/B/C/D compute, 1/3/5/7 = the device-wide barrier after each, 8 =

@@ -104,6 +104,7 @@ SYMBOLS = {
     "ntm_b200_last_kernel_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ntm_b200_last_stream_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ntm_b200_stream_phase_ns": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "ntm_b200_last_backward_ms": (C.c_int32, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ntm_b200_phase_cycles": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "ntm_b200_last_launch_info": (C.c_int32, [C.POINTER(C.c_int32)]),
     "ntm_b200_launch_count": (C.c_int64, []),
@@ -159,6 +160,15 @@ def last_stream_ms():
     steps = C.c_int32(0)
     check(load().ntm_b200_last_stream_ms(buf, C.byref(steps)), "last_stream_ms")
     return {"controller": buf[0], "head_params": buf[1], "memory": buf[2], "init": buf[3], "steps": steps.value}
+
+
+def last_backward_ms():
+    """Training, profiling enabled: device ms of the last ntm_b200_backward_seq
+    ({'memory_backward', 'loop_rest', 'weight_grads', 'total', 'steps'}); steps == 0 if nothing was recorded."""
+    buf = (C.c_float * 4)()
+    steps = C.c_int32(0)
+    check(load().ntm_b200_last_backward_ms(buf, C.byref(steps)), "last_backward_ms")
+    return {"memory_backward": buf[0], "loop_rest": buf[1], "weight_grads": buf[2], "total": buf[3], "steps": steps.value}
 
 
 def stream_phase_ns():

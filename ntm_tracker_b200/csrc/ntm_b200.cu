@@ -107,6 +107,9 @@ __global__ void pack_ao_kernel(const float* __restrict__ aw, const float* __rest
 
 // --------------------------------------------------------------- host side --
 std::atomic<int> g_profiling{0};
+}  // namespace
+bool ntm_b200::profiling_enabled() { return g_profiling.load() != 0; }
+namespace {
 thread_local cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
 thread_local bool g_ev_valid = false;
 thread_local int g_last_info[16] = {0};

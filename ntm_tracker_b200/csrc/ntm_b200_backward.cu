@@ -9,6 +9,7 @@
 // (ntm_b200_gemm_tiles.cuh: d_h = d_raw @ [W_addr|W_out]^T, d_[read|h] = d_z @ W_lstm^T); after the loop the
 // weight gradients X^T @ dZ as large-K tcgen05 GEMMs over all (t, b), the bias gradients (column sums) and
 // the init_state gradients (batch sums through tanh / sigmoid).  Every reduction has a fixed order.
+#include <vector>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -254,6 +255,11 @@ int launch_colsum(const float* src, long long ld, long long nrows, int ncols, fl
 using namespace ntm_b200;
 
 namespace {
+// profiling (ntm_b200_set_profiling): events on the launching stream -- [0] start, per reverse step (before,
+// after) the memory-backward kernel, then end of the reverse loop, end of the call
+thread_local std::vector<cudaEvent_t> g_bev;
+thread_local int g_bev_steps = 0;
+
 bool device_is_sm100() {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
@@ -356,10 +362,23 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
     count_launch();
   }
 
+  const bool prof = profiling_enabled();
+  g_bev_steps = 0;
+  if (prof) {
+    const size_t need = 2 * (size_t)T + 3;
+    while (g_bev.size() < need) {
+      cudaEvent_t ev;
+      BWD_CK(cudaEventCreate(&ev), "cudaEventCreate");
+      g_bev.push_back(ev);
+    }
+    cudaEventRecord(g_bev[0], stream);
+  }
+
   // ---- reverse-time loop ----
   int cur = 0;
   for (long long t = T - 1; t >= 0; --t) {
     float* draw = DMC + (size_t)t * B * PO4;
+    if (prof) cudaEventRecord(g_bev[1 + 2 * (T - 1 - t)], stream);
     st = train::launch_memory_backward(s, B, hist->M_prev + (size_t)t * B * N * M, hist->w_prev + (size_t)t * B * H * N,
                                        hist->params + (size_t)t * B * PO4, dcat[0], y.ncat[0], dwbuf[cur], dM,
                                        dwbuf[cur ^ 1], draw, dlogits, (int)T, (int)t,
@@ -367,6 +386,7 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
                                        (hist->sim && hist->cn) ? hist->cn + (size_t)t * B * M : nullptr, rowDraw, y.pA.KAtot,
                                        stream);
     if (st) return st == NTM_B200_ERR_CUDA ? set_cuda_error_ext(cudaGetLastError(), "mem_backward_kernel") : st;
+    if (prof) cudaEventRecord(g_bev[2 + 2 * (T - 1 - t)], stream);
     cur ^= 1;
     // d_h(top) = d_raw @ [W_addr | W_out]^T, K slices into slabs
     // (the memory-backward kernel has already written d_raw into the row-operand tiles)
@@ -394,6 +414,7 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
     }
   }
   float* dw_final = dwbuf[cur];          // gradient w.r.t. the weightings entering step 0
+  if (prof) cudaEventRecord(g_bev[1 + 2 * T], stream);
 
   // ---- weight gradients: one large-K GEMM per variable over all (t, b) ----
   const dim3 eg(2 * nsm), eb(256);
@@ -452,6 +473,29 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
         bwd::launch_colsum(dcat[0], y.ncat[0], B, RM, g->init_read, state0->read, 1, stream))
       return set_cuda_error_ext(cudaGetLastError(), "colsum(init_state)");
   }
+  if (prof) {
+    cudaEventRecord(g_bev[2 + 2 * T], stream);
+    g_bev_steps = (int)T;
+  }
+  return NTM_B200_OK;
+}
+
+// Profiling enabled (ntm_b200_set_profiling) and the stream synchronised: device ms of this thread's last
+// ntm_b200_backward_seq -- {memory-backward kernel summed over the steps, rest of the reverse loop (GEMMs +
+// LSTM gate backward), weight gradients + init_state sums, whole call}; *steps = 0 if there is nothing to report.
+extern "C" int32_t ntm_b200_last_backward_ms(float* out4, int32_t* steps) {
+  if (!out4 || !steps) return NTM_B200_ERR_NULL_POINTER;
+  out4[0] = out4[1] = out4[2] = out4[3] = 0.0f;
+  *steps = g_bev_steps;
+  if (g_bev_steps <= 0) return NTM_B200_OK;
+  const int T = g_bev_steps;
+  float ms = 0.0f, loop = 0.0f;
+  for (int i = 0; i < T; ++i)
+    if (cudaEventElapsedTime(&ms, g_bev[1 + 2 * i], g_bev[2 + 2 * i]) == cudaSuccess) out4[0] += ms;
+  if (cudaEventElapsedTime(&loop, g_bev[0], g_bev[1 + 2 * T]) == cudaSuccess) out4[1] = loop - out4[0];
+  if (cudaEventElapsedTime(&ms, g_bev[1 + 2 * T], g_bev[2 + 2 * T]) == cudaSuccess) out4[2] = ms;
+  if (cudaEventElapsedTime(&ms, g_bev[0], g_bev[2 + 2 * T]) == cudaSuccess) out4[3] = ms;
+  cudaGetLastError();
   return NTM_B200_OK;
 }
 

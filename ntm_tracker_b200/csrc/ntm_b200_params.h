@@ -104,6 +104,7 @@ struct EnvSwitches {
 };
 EnvSwitches read_env();
 
+bool profiling_enabled();   // ntm_b200_set_profiling state (per-kernel CUDA events on the launching stream)
 void count_launch();   // bumps the library-wide kernel-launch counter (ntm_b200_launch_count)
 namespace k512 { const KernelVariant& variant(); }
 namespace k256 { const KernelVariant& variant(); }

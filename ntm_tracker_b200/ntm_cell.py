@@ -236,18 +236,19 @@ class NTMCell(object):
         return _cabi.State(*ptrs, *strides), keep
 
     # ------------------------------------------------------------------- run --
-    def _run(self, inputs, state, steps, history=None, workspace=None, continuation=False):
+    def _run(self, inputs, state, steps, history=None, workspace=None, continuation=False, out_state=None):
         """inputs [B, steps, D] float32 CUDA contiguous -> (logits, outputs, new_state, taps).
         `workspace`: caller-provided scratch tensor (else cached per geometry).  `continuation`: this call
         advances the sequences of the previous call on the same workspace; `state` (that call's new_state) is
-        updated in place and returned (ntm_b200_forward_seq_continue)."""
+        updated in place and returned (ntm_b200_forward_seq_continue).  `out_state`: dense state buffers (as
+        ``state_placeholder`` makes them) to receive the new state instead of freshly allocated ones."""
         if not torch.cuda.is_available():
             raise RuntimeError("ntm_tracker_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         # the library launches on the CURRENT device with the stream it is handed: pin both to the cell's device
         with torch.cuda.device(self.device):
-            return self._run_on_device(inputs, state, steps, history, workspace, continuation)
+            return self._run_on_device(inputs, state, steps, history, workspace, continuation, out_state)
 
-    def _run_on_device(self, inputs, state, steps, history, workspace, continuation):
+    def _run_on_device(self, inputs, state, steps, history, workspace, continuation, out_state=None):
         lib = _cabi.load()
         B, T, D = inputs.shape
         if T != steps:
@@ -300,6 +301,14 @@ class NTMCell(object):
             if self.debug or history is not None or any(not state[k].is_contiguous() for k in want):
                 raise ValueError("continuation needs a dense state and neither debug taps nor history")
             new_state = state
+        elif out_state is not None:
+            for k, s in want.items():
+                v = out_state[k]
+                if tuple(v.shape) != s or v.device != dev or v.dtype != torch.float32 or not v.is_contiguous():
+                    raise ValueError("out_state['%s'] must be a dense float32 %s tensor on %s" % (k, s, dev))
+                if v.data_ptr() == state[k].data_ptr():
+                    raise ValueError("out_state['%s'] aliases the input state" % k)
+            new_state = {k: out_state[k] for k in want}
         else:
             new_state = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in want.items()}
         sin, keep_in = self._state_struct(state, inner)

@@ -21,6 +21,8 @@ class ResidentTracker(object):
         self.batch_size = int(batch_size)
         self.state = None
         self.frame_index = 0
+        self._spare = [None, None]     # two sets of state buffers, written alternately (no allocation per frame)
+        self._zero_target = None
 
     def reset(self, state=None):
         """Start a new sequence (test_tracker.py:146: ``states=[sess.run(zero_state)]``)."""
@@ -39,8 +41,13 @@ class ResidentTracker(object):
                              % (self.batch_size, self.num_features, tuple(features.shape)))
         B, F, _ = features.shape
         if target is None:
-            target = torch.zeros(B, F, device=features.device)
+            if self._zero_target is None or self._zero_target.device != features.device:
+                self._zero_target = torch.zeros(B, F, device=features.device)
+            target = self._zero_target
         x = tracker_inputs(features.unsqueeze(1), target, delimiter_first=True)     # [B, F+1, Cch+2]
-        logits, _, self.state, _ = self.cell._run(x, self.state, F + 1)
+        slot = self.frame_index & 1
+        if self._spare[slot] is None:
+            self._spare[slot] = self.cell.state_placeholder(B)
+        logits, _, self.state, _ = self.cell._run(x, self.state, F + 1, out_state=self._spare[slot])
         self.frame_index += 1
         return torch.tanh(logits[:, -1])

@@ -176,6 +176,7 @@ def test_time_block_bounds_cover_every_step():
 def test_stream_profiling_hooks_answer_without_a_call(lib):
     """The streaming-mode measurement hooks are safe to call when no streaming call ran on this thread."""
     assert _cabi.last_stream_ms()["steps"] == 0
+    assert _cabi.last_backward_ms()["steps"] == 0
     assert _cabi.stream_phase_ns()["ctas"] == 0
 
 
