@@ -363,6 +363,13 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_cpu=True, want_clo
 
     step_ms, wall, _, _, _, launches, _ = timed_region(False)
     prof_step_ms, _, seq_ms, xp_ms, stream_ms, _, bwd_ms = timed_region(True)
+    info = _cabi.last_launch_info()
+    phase_ns = None
+    if info.get("streaming") and not training:      # in-kernel phase stamps of the last profiled memory-kernel launch
+        try:
+            phase_ns = _cabi.stream_phase_ns()
+        except Exception:
+            phase_ns = None
     lib.ntm_b200_set_profiling(0)
     trk.cell.finish()
     total_ms = max_over_ranks(sum(step_ms), dev)
@@ -388,13 +395,6 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_cpu=True, want_clo
         e2e = {"value": B_total * T * steps / e2e_s, "unit": "seq-steps/s",
                "h2d_bytes_per_step": int(input_bytes) * world, "d2h_bytes_per_step": d2h * world}
     clocks = sampler.stop() if (rank == 0 and want_clocks) else None
-    info = _cabi.last_launch_info()
-    phase_ns = None
-    if info.get("streaming") and not training:
-        try:
-            phase_ns = _cabi.stream_phase_ns()
-        except Exception:
-            phase_ns = None
     del trainer, trk, x_dev, state, flush
     torch.cuda.empty_cache()
     if rank != 0:

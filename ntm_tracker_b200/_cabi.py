@@ -10,7 +10,8 @@ import os
 
 MAX_LAYERS = 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libntm_b200.so")
+# NTM_B200_LIB (development only): another build of the same library, for A/B measurements in one process tree
+LIB_PATH = os.environ.get("NTM_B200_LIB") or os.path.join(_HERE, "libntm_b200.so")
 
 OK = 0
 STATUS_VALUE_ERRORS = (1, 2, 4, 5)   # bad shape / bad shift / heads / too large -> ValueError

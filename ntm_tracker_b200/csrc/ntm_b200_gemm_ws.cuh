@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "ntm_b200_params.h"
@@ -30,7 +31,10 @@
 namespace ntm_b200 {
 namespace gemmws {
 
-constexpr int KA_MAX = 8;            // K atoms (64 wide) per slice: 256 TMEM columns of weight hi halves
+#ifndef NTM_KA_MAX
+#define NTM_KA_MAX 8
+#endif
+constexpr int KA_MAX = NTM_KA_MAX;   // K atoms (64 wide) per slice: 256 TMEM columns of weight hi halves at 8
 constexpr int NSLOT_MAX = 7;         // activation ring slots (32 KiB each): 3 next to a resident weight lo half in
                                      // shared memory, 7 when both weight halves fit TMEM (K slice <= 256)
 constexpr int THREADS = 320;          // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
@@ -350,7 +354,8 @@ inline Plan make_plan(int K, int ncols, long long rows, int nsm) {
   if (g < 1) g = 1;
   p.ngroups = (int)g;
   p.wlo_tmem = (p.KA <= 4) ? 1 : 0;                  // hi + lo halves: 2 * KA * 32 <= 256 TMEM columns
-  p.nslot = p.wlo_tmem ? NSLOT_MAX : 3;
+  // ring slots: whatever the 227 KiB leave next to the resident weight lo half (3 at KA = 8, 4 at KA = 6)
+  p.nslot = p.wlo_tmem ? NSLOT_MAX : std::min(NSLOT_MAX, (B200_SMEM_OPTIN - 1024 - p.KA * ATOM_BYTES) / REC_BYTES);
   p.whi_bytes = (size_t)units * 128 * p.KA * 32 * 4;
   p.wlo_bytes = (size_t)units * p.KA * ATOM_BYTES;
   p.act_bytes = (size_t)nrb * p.KAtot * REC_BYTES;

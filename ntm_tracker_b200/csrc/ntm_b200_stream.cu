@@ -70,7 +70,9 @@ struct MemArgs {
   int WPC;                                   // warps sharing one 8-chunk column group in pass 2
   // TMA-ring kernel: stages of RPS memory rows, NS stages, NCH chunks per pass
   int RPS, NS, NCH, RP, qps_shift;           // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = two stages;
-                                             // qps_shift: log2(2 * NCH) when that is a power of two, else -1
+                                             // qps_shift: log2(stage uses per sequence) when that is a power of two, else -1
+  int NR;                                    // stages of pass 1 that stay in the ring for pass 2 (NS, or 0 = none)
+  unsigned qps_magic;                        // ceil(2^32 / uses per sequence): division by multiplication (0 = divide)
   int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
   int vec_out;                               // read-vector rows are 16-byte aligned
   uint8_t* tilesA; int KAtotA;               // controller-GEMM operand tiles (read vectors at k = r*M + d), or null
@@ -548,21 +550,29 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
 
   // Persistent CTA: sequences b = blockIdx.x + si * gridDim.x.  The ring never drains between sequences:
-  // stage use Qg (global over this CTA's sequences; per sequence NCH pass-1 stages then NCH pass-2 stages)
-  // lives in slot Qg % NS with mbarrier parity (Qg / NS) & 1, and whoever releases use Qg issues the load
-  // of use Qg + NS into the same slot -- so the head of the next sequence streams in behind pass 2.
+  // stage use Qg (global over this CTA's sequences) lives in slot Qg % NS with mbarrier parity (Qg / NS) & 1,
+  // and whoever releases use Qg issues the load of use Qg + NS into the same slot -- so the head of the next
+  // sequence streams in behind pass 2.  Per sequence: NCH pass-1 uses (row stages 0 .. NCH-1, from HBM), then
+  // the pass-2 uses.  The last NR (= NS) stages of pass 1 are NOT released: pass 2 starts with them where they
+  // lie (rows of the stages NCH-NR .. NCH-1) and goes on with the row stages 0 .. NCH-NR-1, re-read through L2
+  // -- a quarter of the re-read traffic and of the lines that must survive in L2 gone at N*M*4 = 256 KiB.  So
+  // pass-2 position p (0 .. NCH-1) is use Qb + NCH - NR + p, and a sequence takes QPS = 2*NCH - NR uses.
   const int G = gridDim.x;
   const int nseq = ((int)a.B - (int)blockIdx.x + G - 1) / G;
-  const int QPS = 2 * NCH, QT = nseq * QPS;
-  // (the division runs on the issuing lane only, ~32 times per sequence; carrying (sequence, use) pairs
+  const int NR = a.NR;
+  const int QPS = 2 * NCH - NR, QT = nseq * QPS;
+  // (the division runs on the issuing lane only, ~28 times per sequence; carrying (sequence, use) pairs
   // instead costs registers this kernel does not have: it spilled and ran 11 % slower)
   auto issue_load = [&](int Qg) {
-    const int si = a.qps_shift >= 0 ? (Qg >> a.qps_shift) : Qg / QPS, Q = Qg - si * QPS;
-    const int j = Q < NCH ? Q : Q - NCH;
+    const int si = a.qps_shift >= 0 ? (Qg >> a.qps_shift)
+                                    : (a.qps_magic != 0u ? (int)__umulhi((unsigned)Qg, a.qps_magic) : Qg / QPS);
+    const int Q = Qg - si * QPS;
+    const int j = Q < NCH ? Q : Q - NCH;      // row stage: pass 1 in order; pass-2 loads start over at stage 0
     const float* src = a.Min + (size_t)(blockIdx.x + si * G) * a.sMin + (size_t)j * stage_floats;
     uint64_t* fb = bars + (Qg & (NS - 1));
     mbar_expect_tx(fb, stage_bytes);
-    bulk_load(ring + (Qg & (NS - 1)) * stage_floats, src, stage_bytes, fb, Q < NCH ? pol_keep : pol_drop, hint);
+    // only the pass-1 stages that pass 2 re-reads through L2 are worth keeping there
+    bulk_load(ring + (Qg & (NS - 1)) * stage_floats, src, stage_bytes, fb, Q < NCH - NR ? pol_keep : pol_drop, hint);
   };
   // head parameters, entering weightings and inverse column norms of sequence si -> shared memory
   const uint32_t par_bytes = (uint32_t)(a.PO4 + H * N + M4) * 4u;
@@ -732,8 +742,11 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           if (lane < 2 * H) simq[g0] = v[0];
         }
         // the team were the stage's only readers: once both members are done, refill the slot with use Qg + NS
-        asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPT) : "memory");
-        if (member == 0 && lane == 0 && Qg + NS < QT) issue_load(Qg + NS);
+        // (the last NR stages stay where they are for pass 2)
+        if (q < NCH - NR) {
+          asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPT) : "memory");
+          if (member == 0 && lane == 0 && Qg + NS < QT) issue_load(Qg + NS);
+        }
       }
     }
     __syncthreads();
@@ -883,11 +896,14 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
       const int RS = 4 * RP;                       // rows per iteration = two stages
       const int qps = RP >> 1;                     // quads per stage
       const int sk = rp >= qps ? 1 : 0;            // which of the iteration's two stages this thread's quad is in
-      int it = 0;
-      for (int nb = 0; nb < N; nb += RS, ++it) {
+      const int NIT = N / RS;                      // iterations = NCH / 2
+      for (int it = 0; it < NIT; ++it) {
+        // position p = 2 * it of pass 2: the stages retained from pass 1 first (rows from stage NCH - NR on), then
+        // the re-read stages 0 .. NCH-NR-1
+        const int nb = (2 * it < NR ? (NCH - NR + 2 * it) : (2 * it - NR)) * RPS;
         const int n0 = nb + 4 * rp;                // this thread's quad
         if (worker && n0 < N) {
-          const int Qg = Qb + NCH + 2 * it + sk;
+          const int Qg = Qb + NCH - NR + 2 * it + sk;
           mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
           const float* mp = ring + (Qg & (NS - 1)) * stage_floats + 4 * (rp - sk * qps) * M + 4 * c;
           float* gp = Mo + (size_t)n0 * M + 4 * c;
@@ -943,7 +959,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         // one bulk copy costs its issuing thread ~240 ns (tools/tma_probe.cu): rotate the issuer over the
         // warps so that no warp pays it twice in a row
         if ((tid & 31) == 0 && ((warp - 2 * it) & (NWARP - 1)) < 2) {   // two issuers, rotating over the warps
-          const int Qn = Qb + NCH + 2 * it + ((warp - 2 * it) & (NWARP - 1)) + NS;
+          const int Qn = Qb + NCH - NR + 2 * it + ((warp - 2 * it) & (NWARP - 1)) + NS;
           if (Qn < QT) issue_load(Qn);
         }
       }
@@ -1153,6 +1169,71 @@ __global__ void lstm_stream_kernel(const LstmArgs a) {
     for (int e = 0; e < 8; ++e) v[e] = __shfl_sync(0xffffffffu, h_new, g0 + e);
     if (live && (lane & 7) == 0) gemmws::store_split8(a.tilesA, a.KAtotA, b, a.koffA + u, v);
     if (live && (lane & 7) == 1) gemmws::store_split8(a.tilesC, a.KAtotC, b, u - 1, v);
+  }
+}
+
+// Same step, four consecutive units per thread (C % 4 == 0, 16-byte aligned rows everywhere): every access is a
+// 16-byte vector -- 4x the bytes in flight per thread of the scalar kernel above, which was latency-bound on the
+// K-slice slabs (33 us per step of 4096 sequences; this one: see DESIGN.md s4.3).  Same summation order.
+__global__ void __launch_bounds__(256) lstm_stream_kernel_v4(const LstmArgs a) {
+  const int C = a.C, C4 = C >> 2;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i0 < a.B * C4;
+  const unsigned ii = live ? (unsigned)i0 : 0u;      // host guarantees B * C4 < 2^31
+  const unsigned bu = ii / (unsigned)C4;
+  const long long b = bu;
+  const int u = 4 * (int)(ii - bu * (unsigned)C4);
+  float4 z[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = q * C + u;
+    z[q] = (a.l == 0) ? __ldg(reinterpret_cast<const float4*>(a.xw + (b * a.T + a.t) * (long long)(4 * C) + col))
+                      : __ldg(reinterpret_cast<const float4*>(a.bias + col));
+  }
+  {
+    const float* pp = a.part + b * (long long)(4 * C) + u;
+#pragma unroll 5
+    for (int ks = 0; ks < a.KS; ++ks) {
+      float4 sl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sl[q] = __ldcg(reinterpret_cast<const float4*>(pp + (size_t)ks * a.slab + q * C));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { z[q].x += sl[q].x; z[q].y += sl[q].y; z[q].z += sl[q].z; z[q].w += sl[q].w; }
+    }
+  }
+  float* cp = a.ctrl + b * a.sctrl + (2 * a.l) * C + u;
+  const float4 c_prev = *reinterpret_cast<const float4*>(cp);
+  float4 c_new, h_new;
+  c_new.x = c_prev.x * sigmoid_f(z[2].x) + sigmoid_f(z[0].x) * tanh_f(z[1].x);
+  c_new.y = c_prev.y * sigmoid_f(z[2].y) + sigmoid_f(z[0].y) * tanh_f(z[1].y);
+  c_new.z = c_prev.z * sigmoid_f(z[2].z) + sigmoid_f(z[0].z) * tanh_f(z[1].z);
+  c_new.w = c_prev.w * sigmoid_f(z[2].w) + sigmoid_f(z[0].w) * tanh_f(z[1].w);
+  h_new.x = tanh_f(c_new.x) * sigmoid_f(z[3].x);
+  h_new.y = tanh_f(c_new.y) * sigmoid_f(z[3].y);
+  h_new.z = tanh_f(c_new.z) * sigmoid_f(z[3].z);
+  h_new.w = tanh_f(c_new.w) * sigmoid_f(z[3].w);
+  if (live) {
+    if (a.hZ) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(a.hZ + ((((size_t)a.t * a.B + b) * a.L + a.l) * 4 + q) * C + u) = z[q];
+    }
+    *reinterpret_cast<float4*>(cp) = c_new;
+    *reinterpret_cast<float4*>(cp + C) = h_new;
+    if (a.hC) *reinterpret_cast<float4*>(a.hC + (((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u) = c_new;
+    if (a.hH) *reinterpret_cast<float4*>(a.hH + (((size_t)(a.t + 1) * a.B + b) * a.L + a.l) * C + u) = h_new;
+    *reinterpret_cast<float4*>(a.act_self + b * a.actK_self + (a.actK_self - C) + u) = h_new;
+    if (a.act_next) *reinterpret_cast<float4*>(a.act_next + b * a.actK_next + u) = h_new;
+  }
+  if (a.tilesA != nullptr) {   // C % 8 == 0: an (even, odd) lane pair holds 8 consecutive units of one sequence
+    const bool odd = (threadIdx.x & 1) != 0;
+    const float px = __shfl_xor_sync(0xffffffffu, h_new.x, 1), py = __shfl_xor_sync(0xffffffffu, h_new.y, 1);
+    const float pz = __shfl_xor_sync(0xffffffffu, h_new.z, 1), pw = __shfl_xor_sync(0xffffffffu, h_new.w, 1);
+    float v[8];
+    v[0] = odd ? px : h_new.x; v[1] = odd ? py : h_new.y; v[2] = odd ? pz : h_new.z; v[3] = odd ? pw : h_new.w;
+    v[4] = odd ? h_new.x : px; v[5] = odd ? h_new.y : py; v[6] = odd ? h_new.z : pz; v[7] = odd ? h_new.w : pw;
+    if (live && !odd) gemmws::store_split8(a.tilesA, a.KAtotA, b, a.koffA + u, v);
+    if (live && odd) gemmws::store_split8(a.tilesC, a.KAtotC, b, u - 4, v);
   }
 }
 
@@ -1461,9 +1542,14 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       ma.NS = TMA_NS;
       ma.RPS = tma_rps(N, M);
       ma.NCH = N / ma.RPS;
+      // stages of pass 1 kept in the ring for pass 2 (needs a whole ring of them; NTM_B200_EXP bit 1 = off)
+      ma.NR = (ma.NCH >= ma.NS && !(env.exp & 2)) ? ma.NS : 0;
+      const int qps = 2 * ma.NCH - ma.NR;          // stage uses per sequence
       ma.qps_shift = -1;
       for (int sh = 0; sh < 30; ++sh)
-        if ((1 << sh) == 2 * ma.NCH) ma.qps_shift = sh;
+        if ((1 << sh) == qps) ma.qps_shift = sh;
+      ma.qps_magic = 0u;                           // exact for Qg * qps < 2^32
+      if ((B + 1) * (long long)qps * qps < (1ll << 32)) ma.qps_magic = (unsigned)(((1ull << 32) + qps - 1) / qps);
       ma.RP = tma_rp(MC);
       ma.oBar = take2(2 * (ma.NS + 1) + 2);
       o2 = round_up(o2, 32);                      // 128-byte aligned ring
@@ -1512,7 +1598,12 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
         la.act_next = (l + 1 < L) ? act[l + 1] : nullptr; la.actK_next = (l + 1 < L) ? ws.actK[l + 1] : 0;
         la.hZ = hist ? hist->z : nullptr; la.hC = hist ? hist->c : nullptr; la.hH = hist ? hist->h : nullptr;
         const long long tot = B * C;
-        lstm_stream_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(la);
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+        const bool v4 = !(env.exp & 4) && C % 4 == 0 && la.actK_self % 4 == 0 && (la.act_next == nullptr || la.actK_next % 4 == 0) &&
+                        la.sctrl % 4 == 0 && al16(la.ctrl) && al16(la.xw) && al16(la.bias) && al16(la.part) && ws.slabA % 4 == 0 &&
+                        al16(la.act_self) && al16(la.act_next) && al16(la.hZ) && al16(la.hC) && al16(la.hH) && tot / 4 < (1ll << 31);
+        if (v4) lstm_stream_kernel_v4<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, stream>>>(la);
+        else lstm_stream_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(la);
         count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "lstm_stream_kernel");
       }

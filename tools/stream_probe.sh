@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/stream_probe.sh <tag> [env assignments...] -- short device-resident bench of the streaming mode
 tag=$1; shift
-env NTM_B200_MODE=stream "$@" timeout 300 python bench.py $BENCH_ARGS --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/probe_$tag.json 2> gpurun_out/probe_$tag.err || tail -5 gpurun_out/probe_$tag.err
+env NTM_B200_MODE=stream "$@" timeout 300 python bench.py $BENCH_ARGS --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-train --no-serve > gpurun_out/probe_$tag.json 2> gpurun_out/probe_$tag.err || tail -5 gpurun_out/probe_$tag.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/probe_$tag.json"))
