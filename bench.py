@@ -257,7 +257,7 @@ def _traffic(workload):
         return None
 
 
-def measure(workload, ctx, steps, warmup, want_e2e=True, want_cpu=True, want_clocks=True, batch=0, seq_len=0):
+def measure(workload, ctx, steps, warmup, want_e2e=True, want_clocks=True, batch=0, seq_len=0):
     """One workload on this rank's GPU: W warm-up steps, K timed steps (CUDA events, max over ranks), a second
     profiled region for the per-kernel durations, the end-to-end leg.  Returns the JSON line (rank 0) or None."""
     import ctypes as C
@@ -480,11 +480,6 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_cpu=True, want_clo
             "smem_peak_gbs": smem_peak, "smem_frac": achieved / smem_peak,
         })
 
-    cpu = None
-    if want_cpu and world == 1:
-        v, cores, sample, _ = cpu_reference_run(cfg_name, 5, 2)
-        cpu = {"value": v, "unit": "seq-steps/s", "cores": cores, "kind": "port", "sample": sample}
-
     return {
         "metric": "sequence_timesteps_per_s", "value": value, "unit": "seq-steps/s",
         "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
@@ -501,7 +496,7 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_cpu=True, want_clo
                                   else "resident (persistent kernel, memory in shared memory)"),
                        **kw),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": None,
         "wall_s_timed_region": wall,
     }
 
@@ -648,13 +643,12 @@ def main():
                             "h2d_bytes_per_step": sv["h2d_bytes_per_frame"], "d2h_bytes_per_step": sv["d2h_bytes_per_frame"]},
                     "serve": sv}
     else:
-        line = measure(args.workload, ctx, args.steps, args.warmup, want_e2e=not args.no_e2e, want_cpu=want_cpu,
+        line = measure(args.workload, ctx, args.steps, args.warmup, want_e2e=not args.no_e2e,
                        batch=args.batch, seq_len=args.seq_len)
         # companion numbers on the default line: the training step (BASELINE configs[4]; the path's only collective,
         # the NCCL gradient all-reduce, runs when N > 1) and the serve path's per-frame latency (rank 0)
         if args.workload == "c3_sweep" and not args.no_train and not args.batch and not args.seq_len:
-            tl = measure("c5_train", ctx, max(3, min(args.steps, 5)), 3, want_e2e=True, want_cpu=False,
-                         want_clocks=False)
+            tl = measure("c5_train", ctx, max(3, min(args.steps, 5)), 3, want_e2e=True, want_clocks=False)
             if line is not None and tl is not None:
                 r = tl["roofline"]
                 line["train"] = {
@@ -670,6 +664,11 @@ def main():
         if args.workload == "c3_sweep" and not args.no_serve and rank == 0 and line is not None:
             line["serve"] = measure_serve(dev, want_cpu)
 
+    # the CPU baseline runs LAST: its 16 busy host threads would otherwise sit next to the GPU legs that follow
+    # (a training e2e measured right after it lost 2.7x to the leftover thread pool)
+    if rank == 0 and line is not None and want_cpu and world == 1 and args.workload in WORKLOADS:
+        v, cores, sample, _ = cpu_reference_run(WORKLOADS[args.workload][0], 5, 2)
+        line["cpu_baseline"] = {"value": v, "unit": "seq-steps/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0 and line is not None:
         emit(line)
     if world > 1:

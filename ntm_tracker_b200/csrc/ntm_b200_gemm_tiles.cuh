@@ -78,30 +78,31 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_tiles_kernel(const Arg
         if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
       }
     }
+    __syncwarp();   // the warp reaches the final CTA barrier as one
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16_f32(128, 128);
+      const uint32_t ring_lo = sw128_desc_lo(smem);     // descriptor low words: slot / half / 16-k step are plain adds
       uint32_t slot = 0, phase = 0;
       for (int k = 0; k < nka; ++k) {
         mbar_wait(&full[slot], phase);
         tcgen05_fence_after();
-        const uint8_t* sRhi = smem + (size_t)slot * 2 * REC_BYTES;   // row operand (B of the MMA)
-        const uint8_t* sRlo = sRhi + ATOM_BYTES;
-        const uint8_t* sChi = sRhi + REC_BYTES;                      // column operand (A of the MMA)
-        const uint8_t* sClo = sChi + ATOM_BYTES;
+        const uint32_t rhi = ring_lo + slot * (uint32_t)(2 * REC_BYTES >> 4);   // row operand (B of the MMA)
+        const uint32_t rlo = rhi + (uint32_t)(ATOM_BYTES >> 4);
+        const uint32_t chi = rhi + (uint32_t)(REC_BYTES >> 4);                  // column operand (A of the MMA)
+        const uint32_t clo = chi + (uint32_t)(ATOM_BYTES >> 4);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          const uint64_t dRhi = make_sw128_desc(sRhi + s * 32), dRlo = make_sw128_desc(sRlo + s * 32);
-          const uint64_t dChi = make_sw128_desc(sChi + s * 32), dClo = make_sw128_desc(sClo + s * 32);
-          mma_ss(tmem, dChi, dRhi, idesc, (k == 0 && s == 0) ? 0u : 1u);
-          mma_ss(tmem, dChi, dRlo, idesc, 1u);
-          mma_ss(tmem, dClo, dRhi, idesc, 1u);
+          mma_ss_lo(tmem, chi + 2u * s, rhi + 2u * s, idesc, (k == 0 && s == 0) ? 0u : 1u);
+          mma_ss_lo(tmem, chi + 2u * s, rlo + 2u * s, idesc, 1u);
+          mma_ss_lo(tmem, clo + 2u * s, rhi + 2u * s, idesc, 1u);
         }
         mma_commit(&empty[slot]);
         if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
       }
       mma_commit(&acc_full);
     }
+    __syncwarp();
   } else {
     const int qd = warp & 3;                            // TMEM lane quarter this warp may access
     const uint32_t lane_addr = (uint32_t)(32 * qd) << 16;

@@ -43,7 +43,7 @@ constexpr int REC_BYTES = 2 * ATOM_BYTES;
 
 struct Args {
   const uint8_t* act;    // [row blocks][KAtot][hi 16 KiB | lo 16 KiB]
-  const uint32_t* whi;   // [tiles][slices][128 cols][KA * 32] packed bf16 pairs (k, k+1)
+  const uint32_t* whi;   // [tiles][slices][KA * 4 16-k steps][128 cols][8] packed bf16 pairs (k, k+1)
   const uint8_t* wlo;    // [tiles][slices][KA][16 KiB swizzled image]
   const float* bias;     // [ncols] or null
   float* out;            // slab ks at out + ks * slab, rows ldo apart
@@ -52,7 +52,13 @@ struct Args {
   int nslot;             // ring slots
   int wlo_tmem;          // 1: weight lo half in TMEM too (KA <= 4; `wlo` then holds packed words like `whi`)
   int exp;               // experiment switches (EnvSwitches::exp)
+  long long* prof;       // development (NTM_B200_EXP bit 8): [grid][8] ns stamps / wait sums, or null
 };
+__device__ __forceinline__ long long ws_gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
@@ -91,7 +97,9 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_trigger();       // the next kernel of the chain may become resident (it waits for this grid before reading)
   const uint32_t tmem = tmem_slot;
+  if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 0] = ws_gtimer();
   const uint32_t tWhi = tmem + 256;                    // accumulators: columns 0..127 and 128..255
   const uint32_t tWlo = tWhi + 128;                    // (wlo_tmem: KA <= 4, so each half takes <= 128 columns)
   const long long nrb = (a.rows + 127) / 128;
@@ -108,56 +116,75 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
     // issuing thread ~240 ns and one thread sustains ~64 GB/s; two copies in flight per slot halve the time a
     // slot spends filling).  Lane 0 alone arms the barrier with the whole record's byte count: the phase cannot
     // complete before that arrive, whatever the order in which the two copies land.
-    const int nissue = (a.exp & 1) ? 1 : 2;
+    // (four lanes with a quarter record each: the copy's flight time is latency + bytes / 64 GB/s per issuing
+    // thread, and with three slots that time is what the MMA warp ends up waiting for)
+    const int nissue = (a.exp & 1) ? 2 : 4;
     if (lane < nissue) {
       uint32_t slot = 0, phase = 0;      // ring position kept incrementally (no division on this thread's path)
-      const uint32_t bytes = nissue == 2 ? ATOM_BYTES : REC_BYTES;
-      const size_t half = nissue == 2 ? (size_t)lane * ATOM_BYTES : 0;
+      const uint32_t bytes = (uint32_t)REC_BYTES / (uint32_t)nissue;
+      const size_t half = (size_t)lane * bytes;
+      long long wsum = 0;
+      pdl_wait();                        // activations are the previous kernel's output
       for (long long rb = group; rb < nrb; rb += a.ngroups) {
         for (int k = 0; k < nka; ++k) {
+          const long long tw = a.prof ? ws_gtimer() : 0;
           mbar_wait(&empty[slot], phase ^ 1u);                     // passes on a fresh barrier
+          if (a.prof) wsum += ws_gtimer() - tw;
           if (lane == 0) mbar_expect_tx(&full[slot], REC_BYTES);
           bulk_g2s(sRing + (size_t)slot * REC_BYTES + half, a.act + ((size_t)rb * a.KAtot + ka0 + k) * REC_BYTES + half, bytes,
                    &full[slot]);
           if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
         }
       }
+      if (a.prof && lane == 0) a.prof[(size_t)blockIdx.x * 8 + 4] = wsum;
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer ----------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16_f32(128, 128);
+      // descriptor low words: ring slot / weight atom / 16-k step are plain adds of (bytes >> 4)
+      const uint32_t ring_lo = sw128_desc_lo(sRing), wlo_lo = sw128_desc_lo(sWlo);
       if (!a.wlo_tmem) mbar_wait(&wbar, 0);   // weight lo half in shared memory (bulk copies)
       mbar_wait(&whibar, 0);     // weight hi (and lo) half in TMEM (stored by the four epilogue warps)
       tcgen05_fence_after();
+      long long wfull = 0, wacc = 0;
+      if (a.prof) a.prof[(size_t)blockIdx.x * 8 + 1] = ws_gtimer();
       uint32_t slot = 0, phase = 0, it = 0;
       for (long long rb = group; rb < nrb; rb += a.ngroups, ++it) {
         const uint32_t ab = it & 1u;
+        const long long ta = a.prof ? ws_gtimer() : 0;
         mbar_wait(&acc_empty[ab], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
+        if (a.prof) wacc += ws_gtimer() - ta;
         tcgen05_fence_after();
         const uint32_t tAcc = tmem + ab * 128;
         for (int k = 0; k < nka; ++k) {
+          const long long tf = a.prof ? ws_gtimer() : 0;
           mbar_wait(&full[slot], phase);
+          if (a.prof) wfull += ws_gtimer() - tf;
           tcgen05_fence_after();
-          const uint8_t* sBhi = sRing + (size_t)slot * REC_BYTES;
-          const uint8_t* sBlo = sBhi + ATOM_BYTES;
+          const uint32_t bhi = ring_lo + slot * (uint32_t)(REC_BYTES >> 4), blo = bhi + (uint32_t)(ATOM_BYTES >> 4);
+          const uint32_t wlo = wlo_lo + (uint32_t)k * (uint32_t)(ATOM_BYTES >> 4);
+          const uint32_t tA = tWhi + (uint32_t)k * 32u, tAl = tWlo + (uint32_t)k * 32u;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const uint64_t dBhi = make_sw128_desc(sBhi + s * 32);
-            const uint64_t dBlo = make_sw128_desc(sBlo + s * 32);
-            const uint64_t dWlo = make_sw128_desc(sWlo + (size_t)k * ATOM_BYTES + s * 32);
-            const uint32_t tA = tWhi + (uint32_t)(k * 64 + s * 16) / 2;
-            mma_ts(tAcc, tA, dBhi, idesc, (k == 0 && s == 0) ? 0u : 1u);
-            mma_ts(tAcc, tA, dBlo, idesc, 1u);
-            if (a.wlo_tmem) mma_ts(tAcc, tWlo + (uint32_t)(k * 64 + s * 16) / 2, dBhi, idesc, 1u);
-            else mma_ss(tAcc, dWlo, dBhi, idesc, 1u);
+          for (int s = 0; s < 4; ++s) {     // 16-k steps: 32 bytes along the swizzled row, 8 TMEM columns
+            mma_ts_lo(tAcc, tA + 8u * s, bhi + 2u * s, idesc, (k == 0 && s == 0) ? 0u : 1u);
+            mma_ts_lo(tAcc, tA + 8u * s, blo + 2u * s, idesc, 1u);
+            if (a.wlo_tmem) mma_ts_lo(tAcc, tAl + 8u * s, bhi + 2u * s, idesc, 1u);
+            else mma_ss_lo(tAcc, wlo + 2u * s, bhi + 2u * s, idesc, 1u);
           }
           mma_commit(&empty[slot]);                                // slot reusable once these MMAs have read it
           if (++slot == (uint32_t)NSLOT) { slot = 0; phase ^= 1u; }
         }
         mma_commit(&acc_full[ab]);
       }
+      if (a.prof) {
+        a.prof[(size_t)blockIdx.x * 8 + 2] = ws_gtimer();
+        a.prof[(size_t)blockIdx.x * 8 + 5] = wfull;
+        a.prof[(size_t)blockIdx.x * 8 + 6] = wacc;
+      }
     }
+    __syncwarp();   // the warp reaches the final CTA barrier as one (a partial warp must not be counted as arrived)
   } else {
     // ------------------------------------------------ epilogue warps ------------------------------
     const int qd = warp & 3;                            // TMEM lane quarter this warp may access
@@ -169,15 +196,15 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
     {
       // 16 k = 8 packed words per step; four steps' loads are issued together (the staging is a chain of L2
       // round trips otherwise, and at small batches it is most of the kernel)
-      auto stage_weights = [&](const uint32_t* src, uint32_t tdst) {
+      auto stage_weights = [&](const uint32_t* src, uint32_t tdst) {   // src: this lane's 8 words of 16-k step 0
         const int nq = nka * 4;
         for (int q0 = 4 * chalf; q0 < nq; q0 += 8) {    // the quarter's two warps alternate blocks of four steps
           uint4 w4[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int q = min(q0 + i, nq - 1);
-            w4[2 * i] = __ldg(reinterpret_cast<const uint4*>(src + q * 8));
-            w4[2 * i + 1] = __ldg(reinterpret_cast<const uint4*>(src + q * 8 + 4));
+            w4[2 * i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * 1024));
+            w4[2 * i + 1] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * 1024 + 4));
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -189,14 +216,16 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
           }
         }
       };
-      stage_weights(a.whi + (wrec * 128 + jl) * (size_t)(a.KA * 32), tWhi + lane_addr);
+      // packed words [weight record][16-k step][128 columns][8 words]: a warp's load covers 1 KiB contiguous
+      stage_weights(a.whi + (wrec * (size_t)(a.KA * 4) * 128 + jl) * 8, tWhi + lane_addr);
       if (a.wlo_tmem)
-        stage_weights(reinterpret_cast<const uint32_t*>(a.wlo) + (wrec * 128 + jl) * (size_t)(a.KA * 32), tWlo + lane_addr);
+        stage_weights(reinterpret_cast<const uint32_t*>(a.wlo) + (wrec * (size_t)(a.KA * 4) * 128 + jl) * 8, tWlo + lane_addr);
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&whibar);
     }
+    pdl_wait();   // the output buffer may still be read by the kernel before this one
     const float bias = (a.bias != nullptr && jcol < a.ncols) ? __ldg(a.bias + jcol) : 0.0f;
     float* outp = a.out + (size_t)ks * a.slab + jcol;
     uint32_t it = 0;
@@ -252,6 +281,7 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 8 + 3] = ws_gtimer();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -302,7 +332,7 @@ static __global__ void pack_act_tiles_kernel(const float* __restrict__ x, long l
   }
 }
 
-// W [K, ncols] (row stride ldw) -> per (tile, slice): hi words [128 cols][KA*32], lo swizzled images [KA][16 KiB].
+// W [K, ncols] (row stride ldw) -> per (tile, slice): hi words [KA*4 steps][128 cols][8], lo swizzled images [KA][16 KiB].
 static __global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int K, int ncols, int ldw, uint32_t* whi,
                                          uint8_t* wlo, int ntiles, int kslices, int KA, int wlo_words) {
   const long long total = (long long)ntiles * kslices * 128 * KA * 8;      // 8-k chunks
@@ -324,9 +354,10 @@ static __global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int
     umma::split_pack_bf16(v[4], v[5], h.z, l.z);
     umma::split_pack_bf16(v[6], v[7], h.w, l.w);
     const size_t wrec = (size_t)tile * kslices + ks;
-    *reinterpret_cast<uint4*>(whi + (wrec * 128 + jl) * (size_t)(KA * 32) + ch * 4) = h;
+    const size_t widx = ((wrec * (size_t)(KA * 4) + (ch >> 1)) * 128 + jl) * 8 + (ch & 1) * 4;
+    *reinterpret_cast<uint4*>(whi + widx) = h;
     if (wlo_words) {   // lo half destined for TMEM: same packed-word layout as the hi half
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(wlo) + (wrec * 128 + jl) * (size_t)(KA * 32) + ch * 4) = l;
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(wlo) + widx) = l;
     } else {
       uint8_t* img = wlo + (wrec * KA + (kl >> 6)) * ATOM_BYTES +
                      (jl >> 3) * 1024 + (jl & 7) * 128 + ((((kl & 63) >> 3) ^ (jl & 7)) << 4);
@@ -366,8 +397,10 @@ inline bool plan_ok(const Plan& p, int nsm) { return p.ntiles * p.kslices <= nsm
 inline int smem_bytes(const Plan& p) { return 1024 + (p.wlo_tmem ? 0 : p.KA * ATOM_BYTES) + p.nslot * REC_BYTES; }
 
 static inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32_t* whi, const uint8_t* wlo, const float* bias,
-                          float* out, int ldo, long long slab, long long rows, cudaStream_t stream, int exp = 0) {
+                          float* out, int ldo, long long slab, long long rows, cudaStream_t stream, int exp = 0,
+                          long long* prof = nullptr, bool pdl = false) {
   Args a{};
+  a.prof = prof;
   a.act = act; a.whi = whi; a.wlo = wlo; a.bias = bias; a.out = out; a.rows = rows; a.slab = slab; a.ldo = ldo;
   a.ncols = p.ncols; a.ntiles = p.ntiles; a.kslices = p.kslices; a.ngroups = p.ngroups; a.KAtot = p.KAtot; a.KA = p.KA;
   a.nslot = p.nslot; a.wlo_tmem = p.wlo_tmem; a.exp = exp;
@@ -382,8 +415,7 @@ static inline cudaError_t launch(const Plan& p, const uint8_t* act, const uint32
       configured[dev] = smem;
     }
   }
-  gemm_ws_kernel<<<p.ntiles * p.kslices * p.ngroups, THREADS, smem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_chain(gemm_ws_kernel, (unsigned)(p.ntiles * p.kslices * p.ngroups), THREADS, (size_t)smem, stream, pdl, a);
 }
 
 }  // namespace gemmws

@@ -104,6 +104,26 @@ struct EnvSwitches {
 };
 EnvSwitches read_env();
 
+// Programmatic dependent launch (the per-timestep kernel chain of the streaming mode): a kernel launched with
+// the attribute may become resident while its predecessor in the stream is still running; everything it does
+// before pdl_wait() (barrier init, TMEM allocation, weight staging -- nothing the predecessor produces) overlaps
+// the predecessor's tail, and pdl_trigger() lets ITS successor do the same.  Both are no-ops in a plain launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 bool profiling_enabled();   // ntm_b200_set_profiling state (per-kernel CUDA events on the launching stream)
 void count_launch();   // bumps the library-wide kernel-launch counter (ntm_b200_launch_count)
 namespace k512 { const KernelVariant& variant(); }

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -85,6 +86,8 @@ struct MemArgs {
 // One CTA = one sequence, one timestep.
 template <int R, int W, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) mem_step_kernel(const MemArgs a) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int H = R + W, NWARP = NT / 32;
   extern __shared__ float4 mem_smem4[];
   float* smem = reinterpret_cast<float*>(mem_smem4);
@@ -590,6 +593,8 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     fence_async_smem();
   }
   __syncthreads();            // barrier inits visible to every thread before anyone polls
+  pdl_trigger();
+  pdl_wait();                 // head parameters, memories, weightings: all written by earlier kernels of the chain
   if (tid == 0 && nseq > 0) {
     issue_params(0);
     for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg);
@@ -1121,6 +1126,8 @@ struct LstmArgs {
   int KAtotA, koffA, KAtotC;
 };
 __global__ void lstm_stream_kernel(const LstmArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i0 < a.B * a.C;
   const long long i = live ? i0 : 0;      // tail lanes recompute element 0 and store nothing
@@ -1176,6 +1183,8 @@ __global__ void lstm_stream_kernel(const LstmArgs a) {
 // 16-byte vector -- 4x the bytes in flight per thread of the scalar kernel above, which was latency-bound on the
 // K-slice slabs (33 us per step of 4096 sequences; this one: see DESIGN.md s4.3).  Same summation order.
 __global__ void __launch_bounds__(256) lstm_stream_kernel_v4(const LstmArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int C = a.C, C4 = C >> 2;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i0 < a.B * C4;
@@ -1241,6 +1250,7 @@ __global__ void __launch_bounds__(256) lstm_stream_kernel_v4(const LstmArgs a) {
 constexpr int MEM_NT = 256;
 thread_local int g_mem_occ = 0;
 thread_local int g_env_mem_ctas_per_sm = 0;   // EnvSwitches::mem_ctas_per_sm of the call in progress
+thread_local bool g_chain_pdl = false;        // launch the memory kernel with the programmatic-dependent-launch attribute
 
 template <int R, int W, int NT, int MINB>
 cudaError_t launch_mem_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
@@ -1256,8 +1266,7 @@ cudaError_t launch_mem_v(const MemArgs& a, long long B, int smem, cudaStream_t s
     }
     g_mem_occ = occs[dev];
   }
-  mem_step_kernel<R, W, NT, MINB><<<(unsigned)B, NT, smem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_chain(mem_step_kernel<R, W, NT, MINB>, (unsigned)B, NT, (size_t)smem, stream, g_chain_pdl, a);
 }
 template <int R, int W>
 cudaError_t launch_mem_rw(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
@@ -1310,8 +1319,7 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
     int per_sm = occ;
     if (g_env_mem_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, g_env_mem_ctas_per_sm));
     const long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
-    mem_step_tma_kernel<R, W, CPL, FULLM><<<(unsigned)grid, TMA_NT, smem, stream>>>(a);
-    return cudaGetLastError();
+    return launch_chain(mem_step_tma_kernel<R, W, CPL, FULLM>, (unsigned)grid, TMA_NT, (size_t)smem, stream, g_chain_pdl, a);
   }
 }
 template <int R, int W>
@@ -1360,6 +1368,35 @@ int tma_cpl(int H, int MC) {
   const int cpl = MC <= 32 ? 1 : (MC <= 64 ? 2 : (MC <= 128 ? 4 : 0));
   if (cpl == 0 || H * cpl > 20) return 0;
   return cpl;
+}
+
+// Development only (NTM_B200_EXP bit 8): per-CTA timestamps of the last controller / head-parameter GEMM launch of a
+// call, printed to stderr at the end of the call (synchronises the stream).
+long long* g_gemm_prof = nullptr;
+long long* gemm_prof_buffer(int which) {
+  if (g_gemm_prof == nullptr && cudaMalloc(&g_gemm_prof, 2 * 256 * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
+  return g_gemm_prof + (size_t)which * 256 * 8;
+}
+void gemm_prof_dump(cudaStream_t stream) {
+  if (g_gemm_prof == nullptr || cudaStreamSynchronize(stream) != cudaSuccess) return;
+  std::vector<long long> h(2 * 256 * 8);
+  if (cudaMemcpy(h.data(), g_gemm_prof, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  for (int w = 0; w < 2; ++w) {
+    double pro = 0, loop = 0, tail = 0, wempty = 0, wfull = 0, wacc = 0; long long first = 0, last = 0; int n = 0;
+    for (int c = 0; c < 256; ++c) {
+      const long long* r = &h[((size_t)w * 256 + c) * 8];
+      if (r[0] == 0 || r[3] == 0) continue;
+      pro += (double)(r[1] - r[0]); loop += (double)(r[2] - r[1]); tail += (double)(r[3] - r[2]);
+      wempty += (double)r[4]; wfull += (double)r[5]; wacc += (double)r[6];
+      first = (n == 0) ? r[0] : std::min(first, r[0]); last = (n == 0) ? r[3] : std::max(last, r[3]);
+      ++n;
+    }
+    if (n > 0)
+      fprintf(stderr, "[gemm_ws prof %s] ctas %d span %.1f us | per CTA: prologue %.1f, MMA issue loop %.1f (waiting full %.1f, "
+              "acc_empty %.1f), tail %.1f us; producer waiting empty %.1f us\n", w == 0 ? "controller" : "head", n,
+              (last - first) / 1e3, pro / n / 1e3, loop / n / 1e3, wfull / n / 1e3, wacc / n / 1e3, tail / n / 1e3, wempty / n / 1e3);
+  }
+  cudaMemset(g_gemm_prof, 0, 2 * 256 * 8 * sizeof(long long));
 }
 
 thread_local std::vector<cudaEvent_t> g_sev;
@@ -1571,6 +1608,9 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       return set_cuda_error_ext(e, "cudaMemsetAsync(prof)");
     g_prof_ptr = ma.prof; g_prof_B = B;
 
+    // programmatic dependent launch along the chain GEMM -> gates -> GEMM -> memory kernel (NTM_B200_EXP bit 16 = off;
+    // with per-kernel profiling events between the launches there is nothing to overlap)
+    const bool pdl = !(env.exp & 16) && !prof;
     for (long long t = 0; t < T; ++t) {
       const bool last = (t == T - 1);
       if (prof) cudaEventRecord(g_sev[2 + 4 * t + 0], stream);
@@ -1578,7 +1618,9 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       for (int l = 0; l < L; ++l) {
         const float* wl = w->lstm_w[l] + (l == 0 ? (size_t)s->input_dim * 4 * C : 0);
         if (ws_ok) {
-          e = gemmws::launch(planA, tilesA, whiA, wloA, nullptr, partA, 4 * C, ws.slabA, B, stream, env.exp);
+          // (the first launch of the call reads weights packed by the kernels just before it: no early start)
+          e = gemmws::launch(planA, tilesA, whiA, wloA, nullptr, partA, 4 * C, ws.slabA, B, stream, env.exp,
+                             (env.exp & 8) ? gemm_prof_buffer(0) : nullptr, pdl && t > 0);
           count_launch();
           if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(controller)");
         } else {
@@ -1602,16 +1644,18 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
         const bool v4 = !(env.exp & 4) && C % 4 == 0 && la.actK_self % 4 == 0 && (la.act_next == nullptr || la.actK_next % 4 == 0) &&
                         la.sctrl % 4 == 0 && al16(la.ctrl) && al16(la.xw) && al16(la.bias) && al16(la.part) && ws.slabA % 4 == 0 &&
                         al16(la.act_self) && al16(la.act_next) && al16(la.hZ) && al16(la.hC) && al16(la.hH) && tot / 4 < (1ll << 31);
-        if (v4) lstm_stream_kernel_v4<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, stream>>>(la);
-        else lstm_stream_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(la);
+        const bool lpdl = pdl && ws_ok;     // (the fallback GEMM before it is not part of the chain protocol)
+        if (v4) e = launch_chain(lstm_stream_kernel_v4, (unsigned)((tot / 4 + 255) / 256), 256u, (size_t)0, stream, lpdl, la);
+        else e = launch_chain(lstm_stream_kernel, (unsigned)((tot + 255) / 256), 256u, (size_t)0, stream, lpdl, la);
         count_launch();
-        if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "lstm_stream_kernel");
+        if (e != cudaSuccess) return set_cuda_error_ext(e, "lstm_stream_kernel");
       }
       if (prof) cudaEventRecord(g_sev[2 + 4 * t + 1], stream);
       // ---- head parameters + logits: one GEMM, bias folded in ----
       float* mc_t = hP ? hist->params + (size_t)t * B * PO4 : mcbuf;
       if (ws_ok) {
-        e = gemmws::launch(planC, tilesC, whiC, wloC, bC, mc_t, PO4, 0, B, stream, env.exp);
+        e = gemmws::launch(planC, tilesC, whiC, wloC, bC, mc_t, PO4, 0, B, stream, env.exp,
+                           (env.exp & 8) ? gemm_prof_buffer(1) : nullptr, pdl);
         count_launch();
         if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(head parameters)");
       } else {
@@ -1641,6 +1685,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       } else {
         ma.read_out = last ? out->read : nullptr; ma.s_read = out->stride_read;
       }
+      g_chain_pdl = pdl && ws_ok;
       e = cpl ? launch_tma(R, W, cpl, ma, B, smem_tma, stream) : launch_mem(R, W, ma, B, smem, stream);
       count_launch();
       if (e != cudaSuccess) return set_cuda_error_ext(e, "mem_step_kernel");
@@ -1653,6 +1698,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
     }
   }
   if (prof) g_sev_steps = (int)T;
+  if (env.exp & 8) gemm_prof_dump(stream);
   return NTM_B200_OK;
 }
 

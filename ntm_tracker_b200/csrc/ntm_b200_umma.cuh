@@ -153,6 +153,30 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same two issues with the shared-memory descriptors passed as their LOW words (sw128_desc_lo): the high word
+// of every K-major SWIZZLE_128B descriptor is the constant SW128_DESC_HI, and the low word of a neighbouring
+// operand is the base's low word plus (byte offset >> 4) -- one integer add per MMA on the issuing thread instead
+// of re-deriving the descriptor (mask, shift, or) from an address.
+constexpr uint32_t SW128_DESC_HI = 0x40004040u;   // SBO 1024 B, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128_desc_lo(const void* smem_ptr) {
+  return ((smem_u32(smem_ptr) & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_DESC_HI)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_DESC_HI)
+      : "memory");
+}
 // all previously issued MMAs of this thread -> arrive on the mbarrier when complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
