@@ -574,14 +574,26 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   // tensor-core kernel (tcgen05, weight tile resident in TMEM + SMEM); fp32 SIMT kernel for shapes it
   // does not cover or when NTM_B200_DISABLE_TC is set
   st = -1;
-  if (!env.disable_tc)
+  bool xw_partial = false;
+  if (mode == 1 && !env.disable_tc) {
+    // streaming mode: pack pass + the warp-specialised GEMM over the first 64*n input columns (the rest join in the
+    // gate kernel); needs the same "continuation" decision stream_forward gets below
+    const StreamResume& rs0 = g_resume_prev;
+    const bool cont0 = want_cont && rs0.workspace == workspace && rs0.batch == batch && rs0.stream == stream_v &&
+                       rs0.M == state_in->M && state_in->M == state_out->M && rs0.packed == packed &&
+                       memcmp(&rs0.shape, shape, sizeof(*shape)) == 0;
+    st = stream_xproj(shape, weights, batch, steps, inputs, xw, swsb, sws, di.nsm, stream, cont0, env);
+    if (st > 0) return st;
+    xw_partial = (st == 0);
+  }
+  if (st < 0 && !env.disable_tc)
     st = ntm_b200::launch_xproj_tc(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
                                    (long long)batch * steps, shape->input_dim, 4 * C, di.nsm, stream);
   g_last_info[12] = (st == 0) ? 1 : 0;
   if (st < 0)
     st = ntm_b200::launch_xproj(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
                                 (long long)batch * steps, shape->input_dim, 4 * C, stream);
-  g_launches++;
+  if (!xw_partial) g_launches++;
   if (st) return set_cuda_error(cudaGetLastError(), "xproj");
 
   if (mode == 1) {
@@ -596,7 +608,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
                       rs.M == state_in->M && state_in->M == state_out->M && rs.packed == packed &&
                       memcmp(&rs.shape, shape, sizeof(*shape)) == 0;
     st = stream_forward(shape, weights, wCp, wCp + (size_t)C * hp.PO4, batch, steps, xw, state_in, state_out,
-                        logits, outputs, history, swsb, sws, di.nsm, stream, prof, cont, env);
+                        logits, outputs, history, swsb, sws, di.nsm, stream, prof, cont, env, xw_partial);
     if (st) return st;
     if (history == nullptr) g_resume = StreamResume{workspace, state_out->M, (long long)batch, *shape, packed, stream_v};
     g_last_info[14] = cont ? 1 : 0;

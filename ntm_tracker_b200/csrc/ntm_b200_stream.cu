@@ -1124,7 +1124,8 @@ struct LstmArgs {
   float *hZ, *hC, *hH;                   // training history (or null)
   uint8_t *tilesA, *tilesC;              // GEMM operand tiles receiving h (C % 8 == 0), or null
   int KAtotA, koffA, KAtotC;
-};
+  const float* xr; const float* wrem; int nrem;   // layer 0: input columns the hoisted projection left out
+};                                                // ([B*T][nrem]) and their weight rows ([nrem][4C]); nrem 0 = none
 __global__ void lstm_stream_kernel(const LstmArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -1139,6 +1140,14 @@ __global__ void lstm_stream_kernel(const LstmArgs a) {
     const int col = q * C + u;
     float v = (a.l == 0) ? __ldg(a.xw + (b * a.T + a.t) * (long long)(4 * C) + col) : __ldg(a.bias + col);
     z[q] = v;
+  }
+  if (a.l == 0 && a.nrem > 0) {
+    const float* xr = a.xr + (b * a.T + a.t) * (long long)a.nrem;
+    for (int c2 = 0; c2 < a.nrem; ++c2) {
+      const float xv = __ldg(xr + c2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) z[q] = fmaf(xv, __ldg(a.wrem + (size_t)c2 * 4 * C + q * C + u), z[q]);
+    }
   }
   // K-slice partials of the controller GEMM, summed in slice order (deterministic); the loads of a slice
   // for all four gates are issued together
@@ -1198,6 +1207,18 @@ __global__ void __launch_bounds__(256) lstm_stream_kernel_v4(const LstmArgs a) {
     const int col = q * C + u;
     z[q] = (a.l == 0) ? __ldg(reinterpret_cast<const float4*>(a.xw + (b * a.T + a.t) * (long long)(4 * C) + col))
                       : __ldg(reinterpret_cast<const float4*>(a.bias + col));
+  }
+  if (a.l == 0 && a.nrem > 0) {
+    const float* xr = a.xr + (b * a.T + a.t) * (long long)a.nrem;
+    for (int c2 = 0; c2 < a.nrem; ++c2) {
+      const float xv = __ldg(xr + c2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(a.wrem + (size_t)c2 * 4 * C + q * C + u));
+        z[q].x = fmaf(xv, wv.x, z[q].x); z[q].y = fmaf(xv, wv.y, z[q].y);
+        z[q].z = fmaf(xv, wv.z, z[q].z); z[q].w = fmaf(xv, wv.w, z[q].w);
+      }
+    }
   }
   {
     const float* pp = a.part + b * (long long)(4 * C) + u;
@@ -1427,6 +1448,62 @@ bool stream_supported(const ntm_b200_shape* s, int nsm) {
   return 4 * fl <= 200 * 1024;
 }
 
+// The hoisted input projection runs on the warp-specialised GEMM when the controller is single-layer with the
+// operand-tile path (as stream_forward decides), and the input width is a whole number of 64-wide K atoms (at most
+// KA_MAX of them) plus at most 8 columns (the tracker's 512 features + delimiter + target channels).
+static bool xproj_ws_shape(const ntm_b200_shape* s, int* xK, int* xrem) {
+  const int C = s->controller_hidden_size, H = s->read_head_size + s->write_head_size, M = s->mem_dim, D = s->input_dim;
+  if (s->controller_num_layers != 1 || M % 8 != 0 || C % 8 != 0 || M % 4 != 0) return false;
+  if (tma_rps(s->mem_size, M) <= 0 || tma_cpl(H, M / 4) <= 0) return false;
+  const int K = D / 64 * 64;
+  if (K < 64 || K / 64 > gemmws::KA_MAX || D - K > 8) return false;
+  if ((4 * C + 127) / 128 > B200_SMS) return false;
+  *xK = K; *xrem = D - K;
+  return true;
+}
+
+namespace {
+// the xrem last columns of the frames, compacted: xr[r][c] = x[r][xK + c]
+__global__ void extract_cols_kernel(const float* __restrict__ x, long long rows, int D, int xK, int nrem, float* __restrict__ xr) {
+  const long long total = rows * nrem;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nrem;
+    const int c = (int)(i - r * nrem);
+    xr[i] = __ldg(x + r * D + xK + c);
+  }
+}
+}  // namespace
+
+int stream_xproj(const ntm_b200_shape* s, const ntm_b200_weights* w, long long B, long long T, const float* x, float* xw,
+                 char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool cont, const EnvSwitches& env) {
+  if (ws.xK <= 0 || env.no_tma_ring || env.old_gemm || (env.exp & 32)) return -1;
+  const int C = s->controller_hidden_size, D = s->input_dim;
+  const long long rows = B * T;
+  const gemmws::Plan px = gemmws::make_plan(ws.xK, 4 * C, rows, nsm);
+  if (!gemmws::plan_ok(px, nsm) || px.kslices != 1) return -1;
+  uint32_t* whiX = reinterpret_cast<uint32_t*>(wsb + ws.off_whiX);
+  uint8_t* wloX = reinterpret_cast<uint8_t*>(wsb + ws.off_wloX);
+  uint8_t* xt = reinterpret_cast<uint8_t*>(wsb + ws.off_xtiles);
+  cudaError_t e;
+  if (!cont) {
+    gemmws::pack_weight_tiles_kernel<<<2 * nsm, 256, 0, stream>>>(w->lstm_w[0], ws.xK, 4 * C, 4 * C, whiX, wloX, px.ntiles,
+                                                                px.kslices, px.KA, px.wlo_tmem);
+    count_launch();
+  }
+  // frames -> operand tiles (rows past B*T of the last block and nothing else are zero-filled by the kernel itself)
+  gemmws::pack_act_tiles_kernel<<<8 * nsm, 256, 0, stream>>>(x, rows, ws.xK, D, xt, px.KAtot, 0);
+  count_launch();
+  if (ws.xrem > 0) {
+    extract_cols_kernel<<<2 * nsm, 256, 0, stream>>>(x, rows, D, ws.xK, ws.xrem, reinterpret_cast<float*>(wsb + ws.off_xr));
+    count_launch();
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "x-projection pack kernels");
+  e = gemmws::launch(px, xt, whiX, wloX, w->lstm_b[0], xw, 4 * C, 0, rows, stream, env.exp);
+  count_launch();
+  if (e != cudaSuccess) return set_cuda_error_ext(e, "gemm_ws(x-projection)");
+  return 0;
+}
+
 void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWorkspace* ws) {
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int H = s->read_head_size + s->write_head_size, S = 2 * s->shift_range + 1;
@@ -1455,11 +1532,23 @@ void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWork
     ws->off_whiC = take((long long)pc.whi_bytes);
     ws->off_wloC = take((long long)pc.wlo_bytes);
   }
+  ws->xK = 0; ws->xrem = 0;
+  ws->off_whiX = ws->off_wloX = ws->off_xtiles = ws->off_xr = 0;
+  gemmws::Plan px{};
+  if (xproj_ws_shape(s, &ws->xK, &ws->xrem)) {
+    px = gemmws::make_plan(ws->xK, 4 * C, B * T, B200_SMS);
+    ws->off_whiX = take((long long)px.whi_bytes);
+    ws->off_wloX = take((long long)px.wlo_bytes);
+  }
   ws->off_partA = take(4ll * ksmax * ws->slabA);
   ws->off_mc = take(4ll * ws->slabC);
   ws->off_cn = take(4ll * B * round_up(s->mem_dim, 4));
   ws->off_prof = take(8ll * 16 * B);
   ws->off_xw = take(4ll * B * T * 4 * C);
+  if (ws->xK > 0) {      // (everything that depends on T stays at the end: see ntm_b200_forward_seq_continue)
+    ws->off_xr = take(4ll * B * T * std::max(1, ws->xrem));
+    ws->off_xtiles = take((long long)px.act_bytes);
+  }
   ws->total = o;
 }
 
@@ -1467,7 +1556,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
                    long long B, long long T, const float* xw, const ntm_b200_state* in,
                    const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
                    char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont,
-                   const EnvSwitches& env) {
+                   const EnvSwitches& env, bool xw_partial) {
   g_env_mem_ctas_per_sm = env.mem_ctas_per_sm;
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W, S = 2 * s->shift_range + 1;
@@ -1635,6 +1724,10 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
           la.tilesA = tilesA; la.tilesC = tilesC; la.KAtotA = planA.KAtot; la.koffA = R * M; la.KAtotC = planC.KAtot;
         }
         la.xw = xw; la.bias = w->lstm_b[l]; la.part = partA;
+        if (l == 0 && xw_partial && ws.xrem > 0) {
+          la.xr = reinterpret_cast<const float*>(wsb + ws.off_xr); la.nrem = ws.xrem;
+          la.wrem = w->lstm_w[0] + (size_t)ws.xK * 4 * C;
+        }
         la.ctrl = out->controller_state; la.sctrl = out->stride_controller_state;
         la.act_self = act[l]; la.actK_self = ws.actK[l];
         la.act_next = (l + 1 < L) ? act[l + 1] : nullptr; la.actK_next = (l + 1 < L) ? ws.actK[l + 1] : 0;
@@ -1643,7 +1736,8 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
         auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
         const bool v4 = !(env.exp & 4) && C % 4 == 0 && la.actK_self % 4 == 0 && (la.act_next == nullptr || la.actK_next % 4 == 0) &&
                         la.sctrl % 4 == 0 && al16(la.ctrl) && al16(la.xw) && al16(la.bias) && al16(la.part) && ws.slabA % 4 == 0 &&
-                        al16(la.act_self) && al16(la.act_next) && al16(la.hZ) && al16(la.hC) && al16(la.hH) && tot / 4 < (1ll << 31);
+                        al16(la.act_self) && al16(la.act_next) && al16(la.hZ) && al16(la.hC) && al16(la.hH) && tot / 4 < (1ll << 31) &&
+                        al16(la.wrem);
         const bool lpdl = pdl && ws_ok;     // (the fallback GEMM before it is not part of the chain protocol)
         if (v4) e = launch_chain(lstm_stream_kernel_v4, (unsigned)((tot / 4 + 255) / 256), 256u, (size_t)0, stream, lpdl, la);
         else e = launch_chain(lstm_stream_kernel, (unsigned)((tot + 255) / 256), 256u, (size_t)0, stream, lpdl, la);

@@ -16,6 +16,10 @@ namespace ntm_b200 {
 struct StreamWorkspace {
   long long off_act[MAXL], off_partA, off_mc, off_cn, off_prof, off_xw, total;
   long long off_tilesA, off_tilesC, off_whiA, off_wloA, off_whiC, off_wloC;   // warp-specialised GEMM operands
+  // hoisted x-projection through the same GEMM: packed W_x, operand tiles of the frames' first xK columns, and the
+  // remaining xrem (< 64, <= 8) columns as a compact side array [B*T][xrem] the gate kernel folds in
+  long long off_whiX, off_wloX, off_xtiles, off_xr;
+  int xK, xrem;                 // 0 / 0 when the shape does not take this path
   long long slabA, slabC;       // floats per K-slice slab
   int ksA[MAXL], ksC;           // K-slices of each controller GEMM / of the head-parameter GEMM
   int actK[MAXL];
@@ -36,7 +40,14 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
                    long long B, long long T, const float* xw, const ntm_b200_state* in,
                    const ntm_b200_state* out, float* logits, float* outputs, const ntm_b200_history* hist,
                    char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont,
-                   const EnvSwitches& env);
+                   const EnvSwitches& env, bool xw_partial = false);   // xw_partial: xw came from stream_xproj
+
+// Hoisted input projection of the streaming mode on the warp-specialised GEMM: xw[b,t,:] = x[b,t,0:xK] @ W_x[0:xK] + b
+// (pack pass -> tile records, then gemm_ws); the last xrem input columns are copied to ws.off_xr and added by the
+// gate kernel of layer 0.  Returns 0 when done, -1 when the shape does not take this path (the caller then runs
+// the tile kernel of ntm_b200_xproj_tc.cuh over all D columns), > 0 = ntm_b200_status.
+int stream_xproj(const ntm_b200_shape* s, const ntm_b200_weights* w, long long B, long long T, const float* x, float* xw,
+                 char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool cont, const EnvSwitches& env);
 
 // profiling (after the stream was synchronised): {controller GEMM + LSTM, head-parameter GEMM, memory
 // kernel, init} summed over the T steps, in ms; returns the number of memory-kernel launches (0 = none)
