@@ -65,6 +65,8 @@ ntm_b200::EnvSwitches ntm_b200::read_env() {
   e.old_gemm = getenv("NTM_B200_OLD_GEMM") != nullptr;
   const char* c = getenv("NTM_B200_MEM_CTAS_PER_SM");
   e.mem_ctas_per_sm = c != nullptr ? atoi(c) : 0;
+  const char* gcap = getenv("NTM_B200_MEM_GRID");
+  e.mem_grid = gcap != nullptr ? atoi(gcap) : 0;
   const char* x = getenv("NTM_B200_EXP");
   e.exp = x != nullptr ? atoi(x) : 0;
   return e;

@@ -100,6 +100,7 @@ struct EnvSwitches {
   bool no_tma_ring;          // NTM_B200_NO_TMA_RING
   bool old_gemm;             // NTM_B200_OLD_GEMM
   int mem_ctas_per_sm;       // NTM_B200_MEM_CTAS_PER_SM (0 = occupancy)
+  int mem_grid;              // NTM_B200_MEM_GRID: cap on the persistent memory kernel's CTAs (0 = none; experiments)
   int exp;                   // NTM_B200_EXP: bit mask of experiment switches (development only; 0 in production)
 };
 EnvSwitches read_env();

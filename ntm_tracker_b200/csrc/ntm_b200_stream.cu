@@ -762,7 +762,60 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     // ---- addressing (ntm_cell.py:140-176): one warp (WPH warps when there are spares) per head.  Every
     //      sweep over the head's N entries handles four entries per lane at a time -- loads, then math,
     //      then stores -- so the four dependent chains (shared-memory load -> SFU -> store) overlap ----
-    {
+    if (N == 128 && S <= 7 && H <= NWARP && (a.sw_out & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0) {
+      // N = 128 (every BASELINE tracker shape): one warp per head, the head's 128 entries live in REGISTERS -- lane L
+      // holds n = 4L .. 4L+3 -- from the similarity to the final weighting: no shared-memory round trip and no
+      // barrier between the five sweeps of the general path below, the circular shift takes the neighbour lanes'
+      // entries by shuffle (3.4 -> ~2 us of a CTA's 29 us per sequence; nothing streams during this phase)
+      if (warp < H) {
+        const int h = warp;
+        const float gate = sG[h], gamma = sGam[h];
+        float kn = 0.0f;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+        const float scale = sBeta[h] / sqrtf(fmaxf(kn, 1e-12f));   // beta / |k|  (ops.py:152, ntm_cell.py:142)
+        const float4 s4 = *reinterpret_cast<const float4*>(simS + h * Npad + 4 * lane);
+        const float4 p4 = *reinterpret_cast<const float4*>(wprevS + h * N + 4 * lane);
+        float x[4] = {s4.x * scale, s4.y * scale, s4.z * scale, s4.w * scale};
+        const float mx = warp_max(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
+        float e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = exp_f(x[u] - mx);
+        const float sum = warp_sum((e[0] + e[1]) + (e[2] + e[3]));
+        const float gs = gate / sum, g1 = 1.0f - gate;          // w_g = g * softmax + (1 - g) * w_prev
+        float win[12];                                           // gated weights of lanes L-1, L, L+1 (circular)
+        win[4] = fmaf(e[0], gs, p4.x * g1); win[5] = fmaf(e[1], gs, p4.y * g1);
+        win[6] = fmaf(e[2], gs, p4.z * g1); win[7] = fmaf(e[3], gs, p4.w * g1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          win[u] = __shfl_sync(0xffffffffu, win[4 + u], (lane + 31) & 31);
+          win[8 + u] = __shfl_sync(0xffffffffu, win[4 + u], (lane + 1) & 31);
+        }
+        float pw[4];
+        auto shift_pow = [&](auto s_tag) {       // circular_shift(x, j)[n] = x[(n + j) mod N], taps j = shift0 .. shift0+S-1
+          constexpr int SS = decltype(s_tag)::value, SH0 = -((SS + 1) / 2);
+          float swv[SS];
+#pragma unroll
+          for (int s2 = 0; s2 < SS; ++s2) swv[s2] = sSw[h * SMAX + s2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float conv = 0.0f;
+#pragma unroll
+            for (int s2 = 0; s2 < SS; ++s2) conv = fmaf(swv[s2], win[4 + u + SH0 + s2], conv);
+            pw[u] = exp2f(gamma * __log2f(conv));   // conv >= 0, gamma >= 1: pow on the SFU; 0 -> 0
+          }
+        };
+        if (S == 3) shift_pow(std::integral_constant<int, 3>{});
+        else if (S == 1) shift_pow(std::integral_constant<int, 1>{});
+        else if (S == 5) shift_pow(std::integral_constant<int, 5>{});
+        else shift_pow(std::integral_constant<int, 7>{});
+        const float psum = warp_sum((pw[0] + pw[1]) + (pw[2] + pw[3]));
+        const float rden = 1.0f / (psum + 1e-3f);   // ntm_cell.py:175-176
+        const float4 wv = make_float4(pw[0] * rden, pw[1] * rden, pw[2] * rden, pw[3] * rden);
+        *reinterpret_cast<float4*>(wnew + h * Npad + 4 * lane) = wv;
+        *reinterpret_cast<float4*>(a.w_out + (size_t)b * a.sw_out + h * N + 4 * lane) = wv;
+      }
+    } else {
       constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
       constexpr bool multi = (NWARP / H) > 0;
       constexpr int U = 4;
@@ -1271,6 +1324,7 @@ __global__ void __launch_bounds__(256) lstm_stream_kernel_v4(const LstmArgs a) {
 constexpr int MEM_NT = 256;
 thread_local int g_mem_occ = 0;
 thread_local int g_env_mem_ctas_per_sm = 0;   // EnvSwitches::mem_ctas_per_sm of the call in progress
+thread_local int g_env_mem_grid = 0;          // EnvSwitches::mem_grid of the call in progress
 thread_local bool g_chain_pdl = false;        // launch the memory kernel with the programmatic-dependent-launch attribute
 
 template <int R, int W, int NT, int MINB>
@@ -1339,7 +1393,8 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
     g_mem_occ = occ;
     int per_sm = occ;
     if (g_env_mem_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, g_env_mem_ctas_per_sm));
-    const long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
+    long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
+    if (g_env_mem_grid > 0) grid = std::min<long long>(grid, g_env_mem_grid);
     return launch_chain(mem_step_tma_kernel<R, W, CPL, FULLM>, (unsigned)grid, TMA_NT, (size_t)smem, stream, g_chain_pdl, a);
   }
 }
@@ -1558,6 +1613,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
                    char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool prof, bool cont,
                    const EnvSwitches& env, bool xw_partial) {
   g_env_mem_ctas_per_sm = env.mem_ctas_per_sm;
+  g_env_mem_grid = env.mem_grid;
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W, S = 2 * s->shift_range + 1;
   const int N = s->mem_size, M = s->mem_dim, M4 = round_up(M, 4), MC = M4 / 4, Npad = round_up(N, 4);
