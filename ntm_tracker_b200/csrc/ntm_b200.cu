@@ -559,8 +559,19 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   e = kv.max_clusters(R, W, hp.CS, hp.Gteam_max * hp.max_teams * hp.CS, smem_bytes, &max_clusters);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveClusters");
   if (max_clusters < nteams) return NTM_B200_ERR_TOO_LARGE;
-  const int G = (int)std::min<long long>(std::min(max_clusters / nteams, hp.Gteam_max),
-                                         (batch + nteams - 1) / nteams);   // resident sequences per team
+  // Clusters per team.  Normally as many as there are sequences (up to what is co-resident).  When that would leave
+  // each CTA more than 256 KiB of projection weights to stream per timestep -- batch 1, the serve path: one tracker,
+  // 65 steps per frame, 10 MB of weights through two CTAs = 188 us per step -- every co-resident cluster is launched
+  // instead: the ones without a sequence of their own ("helpers") take their share of the GEMM / gate phases and keep
+  // their weight tiles in TMEM (33 us per step).  With enough sequences the extra CTAs only make the device-wide
+  // barrier dearer (C1: 0.51 -> 0.59 ms per call with helpers, C2: 1.19 -> 1.24), hence the threshold.
+  // NTM_B200_EXP bit 64: never, bit 128: always.
+  const int Gfull = std::min(max_clusters / nteams, hp.Gteam_max);
+  const int Gseq = (int)std::min<long long>(Gfull, (batch + nteams - 1) / nteams);
+  long long wbytes = 4ll * C * hp.PO4;
+  for (int l = 0; l < L; ++l) wbytes += 4ll * hp.actK[l] * 4 * C;
+  const bool helpers = (env.exp & 128) || (!(env.exp & 64) && wbytes / ((long long)Gseq * hp.CS * nteams) > (256 << 10));
+  const int G = helpers ? Gfull : Gseq;
   const int ncta = G * hp.CS;                                              // CTAs per team
 
   const bool prof = g_profiling.load() != 0;
@@ -639,7 +650,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
     p.bA[l] = weights->lstm_b[l];
   }
   choose_plans(shape, hp, G, ncta, !env.disable_tc, p.gA, &p.gC, &p.use_tc);
-  g_last_info[0] = p.use_tc; g_last_info[1] = G * nteams; g_last_info[2] = ncta * nteams; g_last_info[3] = hp.CS;
+  g_last_info[0] = p.use_tc; g_last_info[1] = (int)std::min<long long>((long long)G * nteams, batch); g_last_info[2] = ncta * nteams; g_last_info[3] = hp.CS;
   g_last_info[4] = p.gA[0].KS; g_last_info[5] = p.gA[0].KW; g_last_info[6] = p.gC.KS; g_last_info[7] = p.gC.KW;
   g_last_info[8] = nteams; g_last_info[9] = kv.threads; g_last_info[10] = kv.ctas_per_sm; g_last_info[11] = smem_bytes;
   p.wC = static_cast<const float*>(packed);

@@ -503,3 +503,32 @@ def test_streaming_fallback_kernels(gemm_path, switch):
     finally:
         os.environ.pop(switch, None)
     assert max(errs.values()) <= TOL, errs
+
+
+@pytest.mark.parametrize("name", ["small_r2w1_l2", "c2_tracker_b2t4", "defaults_r3w3_l3"])
+def test_helper_clusters_match_reference_golden(golden_dir, name, gemm_path):
+    """Resident mode with every co-resident cluster launched although the batch has only a few sequences (what
+    the library does by itself at batch 1 of the tracker shape -- the serve path): clusters without a sequence of
+    their own share the GEMM / gate phases.  Forced here (NTM_B200_EXP bit 128) on the golden cases."""
+    if gemm_path == "stream":
+        pytest.skip("helper clusters belong to the resident kernel")
+    z, s, params = load_case(golden_dir, name)
+    sub = int(z["m_stride"])
+    x = z["inputs"]
+    os.environ["NTM_B200_EXP"] = "128"
+    try:
+        trk = make_tracker(s, params, x.shape[1])
+        out, logits = trk(torch.from_numpy(x).cuda())
+        trk.cell.finish()
+        from ntm_tracker_b200 import _cabi
+        info = _cabi.last_launch_info()
+    finally:
+        os.environ.pop("NTM_B200_EXP", None)
+    assert info["ctas"] > info["sequences_resident"] * info["cluster_size"], info
+    st = trk.final_state
+    assert maxerr(to_np(logits), z["logits"]) <= TOL
+    assert maxerr(to_np(out), z["outputs"]) <= TOL
+    assert maxerr(to_np(st["w"]), z["final_w"]) <= TOL
+    assert maxerr(to_np(st["read"]), z["final_read"]) <= TOL
+    assert maxerr(to_np(st["controller_state"]), z["final_controller_state"]) <= TOL
+    assert maxerr(to_np(st["M"])[:, ::sub, ::sub], z["final_M"]) <= TOL
