@@ -73,6 +73,7 @@ struct MemArgs {
   int RPS, NS, NCH, RP, qps_shift;           // RP: quads of 4 rows per pass-2 iteration (threads = RP * MC) = two stages;
                                              // qps_shift: log2(stage uses per sequence) when that is a power of two, else -1
   int NR;                                    // stages of pass 1 that stay in the ring for pass 2 (NS, or 0 = none)
+  int exp;                                   // experiment switches (EnvSwitches::exp)
   unsigned qps_magic;                        // ceil(2^32 / uses per sequence): division by multiplication (0 = divide)
   int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
   int vec_out;                               // read-vector rows are 16-byte aligned
@@ -550,7 +551,13 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
 #endif
   // pass 1 brings the rows in and wants them to survive in L2 until pass 2 re-reads them; after that
   // re-read, and for the rewritten rows, the next use is a whole timestep (the other sequences) away
-  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+  // (round 2, after a quarter of the re-read moved into the ring: the re-read stages are best loaded with the
+  // NORMAL policy -- 409-413 us per launch against 415-416 with evict-last, 427 with evict-last on half the lines;
+  // NTM_B200_EXP bit 256 brings evict-last back)
+  uint64_t pol_keep;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(pol_keep));
+  const uint64_t pol_drop = l2_policy_evict_first();
+  if (a.exp & 256) pol_keep = l2_policy_evict_last();
 
   // Persistent CTA: sequences b = blockIdx.x + si * gridDim.x.  The ring never drains between sequences:
   // stage use Qg (global over this CTA's sequences) lives in slot Qg % NS with mbarrier parity (Qg / NS) & 1,
@@ -1726,6 +1733,7 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       ma.NCH = N / ma.RPS;
       // stages of pass 1 kept in the ring for pass 2 (needs a whole ring of them; NTM_B200_EXP bit 1 = off)
       ma.NR = (ma.NCH >= ma.NS && !(env.exp & 2)) ? ma.NS : 0;
+      ma.exp = env.exp;
       const int qps = 2 * ma.NCH - ma.NR;          // stage uses per sequence
       ma.qps_shift = -1;
       for (int sh = 0; sh < 30; ++sh)
