@@ -383,14 +383,19 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_clocks=True, batch
             one_step(x_host) if training else trk(x_host, state)
         barrier()
         t0 = time.perf_counter()
+        per_call = []
         for i in range(steps):
+            tc = time.perf_counter()
             if training:
                 one_step(x_host)                  # H2D copy of the frames, train step, D2H of the loss
                 float(last_loss[0])
             else:
                 out_h, log_h = trk(x_host, state)     # H2D copy, kernels, D2H of outputs + logits
                 d2h = int(out_h.numel() + log_h.numel()) * 4
+            per_call.append((time.perf_counter() - tc) * 1e3)
         barrier()
+        if rank == 0:
+            sys.stderr.write("[bench] %s e2e ms per call: %s\n" % (workload, " ".join("%.2f" % v for v in per_call)))
         e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
         e2e = {"value": B_total * T * steps / e2e_s, "unit": "seq-steps/s",
                "h2d_bytes_per_step": int(input_bytes) * world, "d2h_bytes_per_step": d2h * world}

@@ -514,7 +514,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 // FULLM: M == 128 * CPL exactly (the tracker and large-memory shapes).  Row stride, stage size and the thread
 // mapping of pass 2 are then compile-time constants: the inner loops lose their address arithmetic and their
 // column-bound checks (the kernel is issue-bound; a third of its instructions were integer / control).
-template <int R, int W, int CPL, bool FULLM>
+// N128: N == 128 and S <= 7 (every BASELINE tracker shape): the addressing phase keeps a head's weighting in registers.
+// A template parameter rather than a run-time branch: with both addressing variants in one kernel the code grew from
+// 83 KB to 113 KB and the once-per-sequence phases of the OTHER shapes paid for it in instruction-cache misses
+// (C4, N = 1024: addressing 12 -> 25 us per sequence).
+template <int R, int W, int CPL, bool FULLM, bool N128>
 __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a) {
   constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32, NS = TMA_NS;
   extern __shared__ float4 mem_smem4[];
@@ -769,7 +773,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     // ---- addressing (ntm_cell.py:140-176): one warp (WPH warps when there are spares) per head.  Every
     //      sweep over the head's N entries handles four entries per lane at a time -- loads, then math,
     //      then stores -- so the four dependent chains (shared-memory load -> SFU -> store) overlap ----
-    if (N == 128 && S <= 7 && H <= NWARP && (a.sw_out & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0) {
+    if constexpr (N128) {
       // N = 128 (every BASELINE tracker shape): one warp per head, the head's 128 entries live in REGISTERS -- lane L
       // holds n = 4L .. 4L+3 -- from the similarity to the final weighting: no shared-memory round trip and no
       // barrier between the five sweeps of the general path below, the circular shift takes the neighbour lanes'
@@ -1374,8 +1378,8 @@ cudaError_t launch_mem(int R, int W, const MemArgs& a, long long B, int smem, cu
 }
 
 // ---- TMA-ring kernel dispatch ----
-template <int R, int W, int CPL, bool FULLM>
-cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+template <int R, int W, int CPL, bool FULLM, bool N128>
+cudaError_t launch_tma_v2(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
   if constexpr ((R + W) * CPL > 20) {
     return cudaErrorInvalidValue;
   } else {
@@ -1386,10 +1390,10 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
       std::lock_guard<std::mutex> lk(config_mutex());
       const int dev = current_device_slot();
       if (configured[dev] != smem) {
-        cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM, N128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured[dev] = smem;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs[dev], mem_step_tma_kernel<R, W, CPL, FULLM>, TMA_NT, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs[dev], mem_step_tma_kernel<R, W, CPL, FULLM, N128>, TMA_NT, smem);
         if (occs[dev] < 1) occs[dev] = 1;
         int rdev = 0;
         sms[dev] = B200_SMS;
@@ -1402,8 +1406,14 @@ cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t s
     if (g_env_mem_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, g_env_mem_ctas_per_sm));
     long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
     if (g_env_mem_grid > 0) grid = std::min<long long>(grid, g_env_mem_grid);
-    return launch_chain(mem_step_tma_kernel<R, W, CPL, FULLM>, (unsigned)grid, TMA_NT, (size_t)smem, stream, g_chain_pdl, a);
+    return launch_chain(mem_step_tma_kernel<R, W, CPL, FULLM, N128>, (unsigned)grid, TMA_NT, (size_t)smem, stream, g_chain_pdl, a);
   }
+}
+template <int R, int W, int CPL, bool FULLM>
+cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
+  const bool n128 = a.N == 128 && a.S <= 7 && (R + W) <= TMA_NT / 32 && (a.sw_out & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0;
+  return n128 ? launch_tma_v2<R, W, CPL, FULLM, true>(a, B, smem, stream) : launch_tma_v2<R, W, CPL, FULLM, false>(a, B, smem, stream);
 }
 template <int R, int W>
 cudaError_t launch_tma_rw(int CPL, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
