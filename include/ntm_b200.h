@@ -215,6 +215,21 @@ int32_t ntm_b200_serialize_tracker_inputs(const float* features, const float* ta
 int32_t ntm_b200_gather_offsets(const float* logits, float* offsets, int64_t batch, int32_t frames,
                                 int32_t num_features, int32_t output_dim, void* stream);
 
+/* ntm_b200_forward_seq for frames in FEATURE layout: conv features [B, L, F, Cch] + first-frame target map [B, F]
+ * (what direct_offset_output.py:439-500 concatenates / tiles / reshapes into the tracker inputs, and what
+ * test_tracker.py:385-404 builds per frame on the serve path), with shape->input_dim == Cch + 2 and T = L*(F+1)
+ * steps.  In streaming mode at tracker shapes (Cch a whole number of 64-wide K atoms) the serialised rows are never
+ * materialised: the input projection's pack pass reads the 16-byte aligned feature rows where they lie and
+ * synthesises the delimiter / target channels (identical values to ntm_b200_serialize_tracker_inputs followed by
+ * ntm_b200_forward_seq, bit for bit); otherwise the rows are materialised behind the workspace and the call proceeds
+ * as ntm_b200_forward_seq.  Workspace: ntm_b200_features_workspace_bytes (-1 on a bad shape). */
+int64_t ntm_b200_features_workspace_bytes(const ntm_b200_shape* shape, int64_t batch, int32_t frames, int32_t num_features);
+int32_t ntm_b200_forward_seq_features(const ntm_b200_shape* shape, const ntm_b200_weights* weights, const void* packed,
+                                      int64_t batch, int32_t frames, int32_t num_features, const float* features,
+                                      const float* target, int32_t delimiter_first, const ntm_b200_state* state_in,
+                                      const ntm_b200_state* state_out, float* logits, float* outputs, void* workspace,
+                                      int64_t workspace_bytes, void* stream);
+
 /* Host -> device copy of the frames [t0, t1) of every sequence: inputs_host [B, T, D] (page-locked for a
  * truly asynchronous copy) -> frames_dev [B, t1 - t0, D] contiguous, as one strided DMA on `stream`.  Lets a
  * caller that holds the frames on the host (the reference feeds them through feed_dict on every sess.run,

@@ -494,7 +494,7 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
                             const float* inputs, const ntm_b200_state* state_in,
                             const ntm_b200_state* state_out, float* logits, float* outputs,
                             float* debug_taps, const ntm_b200_history* history,
-                            void* workspace, int64_t workspace_bytes, void* stream_v, bool want_cont);
+                            void* workspace, int64_t workspace_bytes, void* stream_v, bool want_cont, const ntm_b200::FeatureSource* fsrc = nullptr);
 
 int32_t ntm_b200_forward_seq_train(const ntm_b200_shape* shape, const ntm_b200_weights* weights,
                                    const void* packed, int64_t batch, int64_t steps,
@@ -519,8 +519,9 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
                             const float* inputs, const ntm_b200_state* state_in,
                             const ntm_b200_state* state_out, float* logits, float* outputs,
                             float* debug_taps, const ntm_b200_history* history,
-                            void* workspace, int64_t workspace_bytes, void* stream_v, bool want_cont) {
-  if (!shape || !weights || !packed || !inputs || !logits || !workspace) return NTM_B200_ERR_NULL_POINTER;
+                            void* workspace, int64_t workspace_bytes, void* stream_v, bool want_cont,
+                            const ntm_b200::FeatureSource* fsrc) {
+  if (!shape || !weights || !packed || (!inputs && !fsrc) || !logits || !workspace) return NTM_B200_ERR_NULL_POINTER;
   int st = check_state(state_in);
   if (st) return st;
   st = check_state(state_out);
@@ -541,7 +542,8 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   StreamWorkspace sws{};
   stream_layout(shape, batch, steps, &sws);
   const int mode = choose_mode(shape, hp, batch, debug_taps != nullptr, di.nsm, env);
-  if (workspace_bytes < (mode ? sws.total + 1024 : ws.total)) return NTM_B200_ERR_WORKSPACE;
+  const long long ws_need = mode ? sws.total + 1024 : ws.total;
+  if (workspace_bytes < ws_need) return NTM_B200_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   char* wsb = static_cast<char*>(workspace);
   cudaError_t e;
@@ -595,9 +597,21 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
     const bool cont0 = want_cont && rs0.workspace == workspace && rs0.batch == batch && rs0.stream == stream_v &&
                        rs0.M == state_in->M && state_in->M == state_out->M && rs0.packed == packed &&
                        memcmp(&rs0.shape, shape, sizeof(*shape)) == 0;
-    st = stream_xproj(shape, weights, batch, steps, inputs, xw, swsb, sws, di.nsm, stream, cont0, env);
+    st = stream_xproj(shape, weights, batch, steps, inputs, xw, swsb, sws, di.nsm, stream, cont0, env, fsrc);
     if (st > 0) return st;
     xw_partial = (st == 0);
+  }
+  if (fsrc != nullptr && !xw_partial) {
+    // feature-layout call on a path that wants serialised rows (resident mode, shapes the streaming projection does
+    // not cover): materialise them behind the workspace proper (ntm_b200_features_workspace_bytes reserves the room)
+    const long long xbytes = 4ll * batch * steps * shape->input_dim;
+    const long long xoff = (ws_need + 255) / 256 * 256;
+    if (workspace_bytes < xoff + xbytes) return NTM_B200_ERR_WORKSPACE;
+    float* xmat = reinterpret_cast<float*>(wsb + xoff);
+    const int sst = ntm_b200_serialize_tracker_inputs(fsrc->features, fsrc->target, xmat, batch, fsrc->L, fsrc->F, fsrc->Cch,
+                                                      fsrc->delimiter_first, stream_v);
+    if (sst) return sst;
+    inputs = xmat;      // (st stays -1: the projection over the materialised rows runs below)
   }
   if (st < 0 && !env.disable_tc)
     st = ntm_b200::launch_xproj_tc(inputs, weights->lstm_w[0], weights->lstm_b[0], xw,
@@ -696,6 +710,26 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
     g_ev_valid = true;
   }
   return NTM_B200_OK;
+}
+
+int64_t ntm_b200_features_workspace_bytes(const ntm_b200_shape* shape, int64_t batch, int32_t frames, int32_t num_features) {
+  if (!shape || batch < 1 || frames < 1 || num_features < 1) return -1;
+  ntm_b200_plan plan{};
+  const int64_t steps = (int64_t)frames * (num_features + 1);
+  if (ntm_b200_query(shape, batch, steps, &plan) != NTM_B200_OK) return -1;
+  return (plan.workspace_bytes + 255) / 256 * 256 + 4ll * batch * steps * shape->input_dim + 256;
+}
+
+int32_t ntm_b200_forward_seq_features(const ntm_b200_shape* shape, const ntm_b200_weights* weights, const void* packed,
+                                      int64_t batch, int32_t frames, int32_t num_features, const float* features,
+                                      const float* target, int32_t delimiter_first, const ntm_b200_state* state_in,
+                                      const ntm_b200_state* state_out, float* logits, float* outputs, void* workspace,
+                                      int64_t workspace_bytes, void* stream_v) {
+  if (!shape || !features || !target) return NTM_B200_ERR_NULL_POINTER;
+  if (frames < 1 || num_features < 1 || shape->input_dim < 3) return NTM_B200_ERR_BAD_SHAPE;
+  ntm_b200::FeatureSource fs{features, target, frames, num_features, shape->input_dim - 2, delimiter_first ? 1 : 0};
+  return forward_impl(shape, weights, packed, batch, (int64_t)frames * (num_features + 1), nullptr, state_in, state_out, logits,
+                      outputs, nullptr, nullptr, workspace, workspace_bytes, stream_v, false, &fs);
 }
 
 int32_t ntm_b200_step(const ntm_b200_shape* shape, const ntm_b200_weights* weights,

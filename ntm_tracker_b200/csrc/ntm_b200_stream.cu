@@ -1544,11 +1544,60 @@ __global__ void extract_cols_kernel(const float* __restrict__ x, long long rows,
     xr[i] = __ldg(x + r * D + xK + c);
   }
 }
+// Feature-layout source (FeatureSource): row r = (b, t), t = l * (F+1) + pos; the delimiter row of a frame is pos == F
+// (training layout) or pos == 0 (serve layout); feature f of frame l sits at pos f (resp. f + 1).  Same values, bit
+// for bit, as serialize_kernel (ntm_b200_io.cu) followed by pack_act_tiles_kernel / extract_cols_kernel.
+__global__ void pack_feature_tiles_kernel(const float* __restrict__ feat, long long rows, int L, int F, int Cch, int dfirst,
+                                          uint8_t* tiles, int KAtot) {
+  const long long nrb = (rows + 127) / 128;
+  const int T = L * (F + 1);
+  const long long total = nrb * 128 * (long long)KAtot * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i & 7);
+    long long t2 = i >> 3;
+    const int row = (int)(t2 & 127); t2 >>= 7;
+    const int ka = (int)(t2 % KAtot);
+    const long long rb = t2 / KAtot;
+    const long long r = rb * 128 + row;
+    const int k = ka * 64 + chunk * 8;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (r < rows) {
+      const long long b = r / T;
+      const int t = (int)(r - b * T);
+      const int l = t / (F + 1), pos = t - l * (F + 1);
+      const bool is_delim = dfirst ? (pos == 0) : (pos == F);
+      if (!is_delim) {
+        const int f = dfirst ? pos - 1 : pos;
+        const float4* src = reinterpret_cast<const float4*>(feat + (((b * L + l) * F + f) * (long long)Cch + k));
+        v0 = __ldg(src); v1 = __ldg(src + 1);
+      }
+    }
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    gemmws::store_split8(tiles, KAtot, r, k, v);
+  }
+}
+// the two synthesised channels: xr[r] = {delimiter flag, first-frame target on the feature rows}
+__global__ void synth_cols_kernel(const float* __restrict__ target, long long rows, int L, int F, int dfirst, float* __restrict__ xr) {
+  const int T = L * (F + 1);
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    const int l = t / (F + 1), pos = t - l * (F + 1);
+    const bool is_delim = dfirst ? (pos == 0) : (pos == F);
+    const int f = dfirst ? pos - 1 : pos;
+    xr[2 * r] = is_delim ? 1.0f : 0.0f;
+    xr[2 * r + 1] = (l == 0 && !is_delim) ? __ldg(target + b * F + f) : 0.0f;
+  }
+}
 }  // namespace
 
 int stream_xproj(const ntm_b200_shape* s, const ntm_b200_weights* w, long long B, long long T, const float* x, float* xw,
-                 char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool cont, const EnvSwitches& env) {
+                 char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool cont, const EnvSwitches& env,
+                 const FeatureSource* fs) {
   if (ws.xK <= 0 || env.no_tma_ring || env.old_gemm || (env.exp & 32)) return -1;
+  if (fs != nullptr && (fs->Cch != ws.xK || ws.xrem != 2 || (long long)fs->L * (fs->F + 1) != T ||
+                        (reinterpret_cast<uintptr_t>(fs->features) & 15) != 0))
+    return -1;
   const int C = s->controller_hidden_size, D = s->input_dim;
   const long long rows = B * T;
   const gemmws::Plan px = gemmws::make_plan(ws.xK, 4 * C, rows, nsm);
@@ -1563,11 +1612,19 @@ int stream_xproj(const ntm_b200_shape* s, const ntm_b200_weights* w, long long B
     count_launch();
   }
   // frames -> operand tiles (rows past B*T of the last block and nothing else are zero-filled by the kernel itself)
-  gemmws::pack_act_tiles_kernel<<<8 * nsm, 256, 0, stream>>>(x, rows, ws.xK, D, xt, px.KAtot, 0);
-  count_launch();
-  if (ws.xrem > 0) {
-    extract_cols_kernel<<<2 * nsm, 256, 0, stream>>>(x, rows, D, ws.xK, ws.xrem, reinterpret_cast<float*>(wsb + ws.off_xr));
+  if (fs != nullptr) {
+    pack_feature_tiles_kernel<<<8 * nsm, 256, 0, stream>>>(fs->features, rows, fs->L, fs->F, fs->Cch, fs->delimiter_first ? 1 : 0,
+                                                          xt, px.KAtot);
+    synth_cols_kernel<<<2 * nsm, 256, 0, stream>>>(fs->target, rows, fs->L, fs->F, fs->delimiter_first ? 1 : 0,
+                                                  reinterpret_cast<float*>(wsb + ws.off_xr));
+    count_launch(); count_launch();
+  } else {
+    gemmws::pack_act_tiles_kernel<<<8 * nsm, 256, 0, stream>>>(x, rows, ws.xK, D, xt, px.KAtot, 0);
     count_launch();
+    if (ws.xrem > 0) {
+      extract_cols_kernel<<<2 * nsm, 256, 0, stream>>>(x, rows, D, ws.xK, ws.xrem, reinterpret_cast<float*>(wsb + ws.off_xr));
+      count_launch();
+    }
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "x-projection pack kernels");
   e = gemmws::launch(px, xt, whiX, wloX, w->lstm_b[0], xw, 4 * C, 0, rows, stream, env.exp);

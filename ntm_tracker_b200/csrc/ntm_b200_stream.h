@@ -46,8 +46,15 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
 // (pack pass -> tile records, then gemm_ws); the last xrem input columns are copied to ws.off_xr and added by the
 // gate kernel of layer 0.  Returns 0 when done, -1 when the shape does not take this path (the caller then runs
 // the tile kernel of ntm_b200_xproj_tc.cuh over all D columns), > 0 = ntm_b200_status.
+// `fs` (may be null): the frames arrive as conv features [B, L, F, Cch] + first-frame target map [B, F] instead of
+// serialised rows x [B, T, Cch+2] (x is ignored then): the pack pass reads the feature rows where they lie (16-byte
+// loads: Cch-wide rows are aligned, the 514-wide serialised ones are not) and synthesises the delimiter / target
+// channels into the side array -- the tf.concat / tile / reshape chain of direct_offset_output.py:439-500 never
+// materialises.  Needs Cch == xK (else -1).
+struct FeatureSource { const float* features; const float* target; int L, F, Cch, delimiter_first; };
 int stream_xproj(const ntm_b200_shape* s, const ntm_b200_weights* w, long long B, long long T, const float* x, float* xw,
-                 char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool cont, const EnvSwitches& env);
+                 char* wsb, const StreamWorkspace& ws, int nsm, cudaStream_t stream, bool cont, const EnvSwitches& env,
+                 const FeatureSource* fs = nullptr);
 
 // profiling (after the stream was synchronised): {controller GEMM + LSTM, head-parameter GEMM, memory
 // kernel, init} summed over the T steps, in ms; returns the number of memory-kernel launches (0 = none)

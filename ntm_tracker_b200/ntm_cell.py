@@ -337,6 +337,78 @@ class NTMCell(object):
         self._last_ws = ws
         return logits, outputs, new_state, taps
 
+    def _run_features(self, features, target, state, delimiter_first=False, out_state=None):
+        """Frames in feature layout -- features [B, L, F, Cch] (CUDA), target [B, F] -- through
+        ntm_b200_forward_seq_features: T = L*(F+1) steps with the delimiter / target channels synthesised by the
+        library (direct_offset_output.py:439-500; serve layout test_tracker.py:385-404 when `delimiter_first`).
+        Returns (logits, outputs, new_state) like ``_run``."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("ntm_tracker_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        if features.dim() != 4 or target.dim() != 2 or tuple(target.shape) != (features.shape[0], features.shape[2]):
+            raise ValueError("expected features [B,L,F,C] and target [B,F], got %s and %s"
+                             % (tuple(features.shape), tuple(target.shape)))
+        dev = self.device
+        with torch.cuda.device(dev):
+            lib = _cabi.load()
+            features = features.to(dev, torch.float32).contiguous()
+            target = target.to(dev, torch.float32).contiguous()
+            B, L, F, Cch = features.shape
+            D, T = Cch + 2, L * (F + 1)
+            if self.input_dim is None:
+                self.build(D)
+            if D != self.input_dim:
+                raise ValueError("features have %d channels (+2), the cell was built for input width %d" % (Cch, self.input_dim))
+            shp = self._shape_struct(D)
+            plan = _cabi.Plan()
+            _cabi.check(lib.ntm_b200_query(C.byref(shp), B, T, C.byref(plan)), "query")
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            wts = self._weights_struct()
+            if self._dirty or self._packed is None:
+                self._packed = torch.empty(int(plan.packed_bytes), dtype=torch.uint8, device=dev)
+                _cabi.check(lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), self._packed.data_ptr(),
+                                                      self._packed.numel(), stream), "pack_weights")
+                self._dirty = False
+            need = int(lib.ntm_b200_features_workspace_bytes(C.byref(shp), B, L, F))
+            if need < 0:
+                raise ValueError("bad shape for the feature-layout call")
+            ws = self._ws.get(("features", B, L, F))
+            if ws is None or ws.numel() < need:
+                self.finish()
+                ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                self._ws = {("features", B, L, F): ws}
+            H, R, N, M = self.num_heads, self.read_head_size, self.mem_size, self.mem_dim
+            CL2 = 2 * self.controller_hidden_size * self.controller_num_layers
+            inner = {"M": N * M, "w": H * N, "read": R * M, "controller_state": CL2}
+            want = {"M": (B, N, M), "w": (B, H, N), "read": (B, R, M), "controller_state": (B, CL2)}
+            conv = {}
+            for k, sshape in want.items():
+                v = state[k]
+                if not torch.is_tensor(v):
+                    v = torch.as_tensor(np.asarray(v))
+                if tuple(v.shape) != sshape:
+                    raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(v.shape), sshape))
+                conv[k] = v.to(dev, torch.float32)
+            if out_state is not None:
+                for k, sshape in want.items():
+                    v = out_state[k]
+                    if tuple(v.shape) != sshape or v.device != dev or v.dtype != torch.float32 or not v.is_contiguous() \
+                            or v.data_ptr() == conv[k].data_ptr():
+                        raise ValueError("out_state['%s'] must be a dense float32 %s tensor on %s, distinct from the input"
+                                         % (k, sshape, dev))
+                new_state = {k: out_state[k] for k in want}
+            else:
+                new_state = {k: torch.empty(sshape, dtype=torch.float32, device=dev) for k, sshape in want.items()}
+            sin, keep_in = self._state_struct(conv, inner)
+            sout, keep_out = self._state_struct(new_state, inner)
+            logits = torch.empty(B, T, self.output_dim, dtype=torch.float32, device=dev)
+            outputs = torch.empty_like(logits)
+            _cabi.check(lib.ntm_b200_forward_seq_features(
+                C.byref(shp), C.byref(wts), self._packed.data_ptr(), B, L, F, features.data_ptr(), target.data_ptr(),
+                int(bool(delimiter_first)), C.byref(sin), C.byref(sout), logits.data_ptr(), outputs.data_ptr(),
+                ws.data_ptr(), ws.numel(), stream), "forward_seq_features")
+            self._last_ws = ws
+            return logits, outputs, new_state
+
     def finish(self):
         """Synchronise and surface device-side failures of earlier calls."""
         lib = _cabi.load()

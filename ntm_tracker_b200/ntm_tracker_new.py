@@ -86,6 +86,24 @@ class LoopNTMTracker(object):
                 outputs, logits = outputs.numpy(), logits.numpy()
         return (outputs, logits)
 
+    def call_features(self, features, target, delimiter_first=False, state=None):
+        """The same loop for frames in FEATURE layout: features [B, L, F, Cch] (conv4_3 vectors at the F sampled points
+        of each of L frames, CUDA) and target [B, F] (first-frame ground-truth map) -- what the reference's trainer
+        concatenates / tiles / reshapes into ``inputs`` before calling the tracker (direct_offset_output.py:439-500).
+        Here the delimiter and target channels are synthesised inside the library (streaming mode: by the input
+        projection's pack pass, the serialised [B, T, Cch+2] rows never exist).  T = L*(F+1) must equal
+        ``sequence_length``.  Returns (outputs, output_logits) on the device, bit-identical to
+        ``self(serialize.tracker_inputs(features, target, delimiter_first))``."""
+        B, L, F, Cch = features.shape
+        if L * (F + 1) != self.sequence_length:
+            raise ValueError("features hold %d steps but sequence_length is %d" % (L * (F + 1), self.sequence_length))
+        if self.cell.input_dim is None:
+            self.cell.build(Cch + 2, self.initializer)
+        state = state or self.cell.zero_state(B, self.initializer)
+        logits, outputs, new_state = self.cell._run_features(features, target, state, delimiter_first)
+        self.final_state = new_state
+        return (outputs, logits)
+
     # Host-resident frames (page-locked torch tensor): the call is cut into blocks of timesteps and the
     # upload of block i+1 (one strided DMA, ntm_b200_copy_frames_h2d) overlaps the kernels of block i; the
     # state is carried from block to block on the device, every sequence stays in every launch, so the

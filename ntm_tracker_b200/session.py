@@ -11,7 +11,6 @@ leaves the GPU between frames.
 import torch
 
 from .ntm_cell import NTMCell
-from .serialize import tracker_inputs
 
 
 class ResidentTracker(object):
@@ -44,10 +43,11 @@ class ResidentTracker(object):
             if self._zero_target is None or self._zero_target.device != features.device:
                 self._zero_target = torch.zeros(B, F, device=features.device)
             target = self._zero_target
-        x = tracker_inputs(features.unsqueeze(1), target, delimiter_first=True)     # [B, F+1, Cch+2]
         slot = self.frame_index & 1
         if self._spare[slot] is None:
             self._spare[slot] = self.cell.state_placeholder(B)
-        logits, _, self.state, _ = self.cell._run(x, self.state, F + 1, out_state=self._spare[slot])
+        # feature-layout call: the library builds the [delimiter | 64 feature rows] steps itself (serve layout)
+        logits, _, self.state = self.cell._run_features(features.unsqueeze(1), target, self.state, delimiter_first=True,
+                                                        out_state=self._spare[slot])
         self.frame_index += 1
         return torch.tanh(logits[:, -1])

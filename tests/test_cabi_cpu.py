@@ -206,3 +206,18 @@ def test_execution_mode_choice(lib, monkeypatch):
     monkeypatch.setenv("NTM_B200_STREAM_MIN_BATCH", "1000")
     assert mode(shape(), 512) == 0 and mode(shape(), 1001) == 1
     assert lib.ntm_b200_query_mode(C.byref(shape()), 0, C.byref(C.c_int32())) == 1
+
+
+def test_feature_layout_entry_point_argument_checks(lib):
+    """ntm_b200_forward_seq_features / ntm_b200_features_workspace_bytes: shape errors come back as codes (or -1),
+    and without an sm_100 device the compute call answers NTM_B200_ERR_NO_DEVICE like every other entry point."""
+    shp = _cabi.Shape(514, 2, 128, 512, 1, 200, 1, 1, 4, 0)
+    base = _cabi.Plan()
+    assert lib.ntm_b200_query(C.byref(shp), 8, 2 * 65, C.byref(base)) == 0
+    need = lib.ntm_b200_features_workspace_bytes(C.byref(shp), 8, 2, 64)
+    assert need >= base.workspace_bytes + 8 * 130 * 514 * 4         # room for the materialised rows as a fallback
+    assert lib.ntm_b200_features_workspace_bytes(C.byref(shp), 0, 2, 64) == -1
+    assert lib.ntm_b200_features_workspace_bytes(None, 8, 2, 64) == -1
+    wts, st = _cabi.Weights(), _cabi.State()
+    assert lib.ntm_b200_forward_seq_features(C.byref(shp), C.byref(wts), None, 8, 2, 64, None, None, 0, C.byref(st),
+                                             C.byref(st), None, None, None, 0, None) == 3     # null pointers

@@ -114,3 +114,31 @@ def test_resident_tracker_session_matches_stepwise_oracle():
         assert np.abs(got - np.tanh(lg)).max() <= 1e-4
     for k in ("M", "w", "read"):
         assert np.abs(sess.state[k].cpu().numpy() - state[k]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["stream", "resident"])
+@pytest.mark.parametrize("B,L,F,first", [(130, 2, 7, False), (3, 1, 64, True), (129, 3, 3, True)])
+def test_feature_layout_call_is_bit_identical_to_serialised_call(B, L, F, first, mode, monkeypatch):
+    """ntm_b200_forward_seq_features (delimiter / target channels synthesised inside the library; in streaming mode
+    by the input projection's pack pass, without ever materialising the [B, T, 514] rows) against the serialiser
+    followed by the ordinary call: logits, outputs and the final state must agree bit for bit, in both layouts
+    (direct_offset_output.py:439-500, test_tracker.py:385-404) and both execution modes."""
+    from ntm_tracker_b200 import LoopNTMTracker
+    from ntm_tracker_b200.serialize import tracker_inputs
+    monkeypatch.setenv("NTM_B200_MODE", mode)
+    Cch, T = 512, L * (F + 1)
+    rng = np.random.RandomState(B + 7 * L + F)
+    feat = torch.from_numpy(np.maximum(rng.standard_normal((B, L, F, Cch)), 0).astype(np.float32)).cuda()
+    tgt = torch.from_numpy((rng.rand(B, F) < 0.3).astype(np.float32)).cuda()
+    torch.manual_seed(5)
+    trk = LoopNTMTracker(T, 2, mem_size=128, mem_dim=512, controller_hidden_size=200, controller_num_layers=1,
+                         write_head_size=1, read_head_size=4)
+    trk.cell.build(Cch + 2)
+    out_a, log_a = trk(tracker_inputs(feat, tgt, delimiter_first=first))
+    st_a = {k: v.clone() for k, v in trk.final_state.items()}
+    out_b, log_b = trk.call_features(feat, tgt, delimiter_first=first)
+    trk.cell.finish()
+    assert torch.equal(log_a, log_b) and torch.equal(out_a, out_b)
+    for k in st_a:
+        assert torch.equal(st_a[k], trk.final_state[k]), k
+    assert torch.isfinite(log_b).all()
