@@ -248,11 +248,17 @@ def _peaks():
     return peaks, hbm_peak, peak_src
 
 
-def _traffic(workload):
+def _traffic(workload, units_per_launch=None):
     """ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (profiles/traffic.json,
-    which names the capture each figure comes from), or None."""
+    which names the capture each figure comes from), or None.  The capture is of a launch over
+    `<workload>_units_per_launch` sequences; a launch over a different number (a rank's shard) is charged in proportion."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        t = d.get(workload)
+        cap = d.get(workload + "_units_per_launch")
+        if t is not None and cap and units_per_launch and units_per_launch != cap:
+            t = t * float(units_per_launch) / float(cap)
+        return t
     except Exception:
         return None
 
@@ -411,7 +417,7 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_clocks=True, batch
     abytes = algorithmic_bytes_per_seqstep(kw)
     step_avg = sum(prof_step_ms) / len(prof_step_ms)
     ms_per_step = total_ms / steps
-    traffic = _traffic(workload)
+    traffic = _traffic(workload, B_local)
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     smem_peak = 128.0 * 148 * sm_mhz * 1e6 / 1e9          # 128 B/clk/SM at the sampled SM clock
     streaming = bool(info.get("streaming"))
