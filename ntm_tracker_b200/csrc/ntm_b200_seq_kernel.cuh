@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "ntm_b200_params.h"
 #include "ntm_b200_umma.cuh"
@@ -659,7 +660,59 @@ __device__ __forceinline__ void phase_d(const KParams& p, cg::cluster_group& clu
   // ---- addressing on the full [H][N] weighting, replicated in every CTA (ntm_cell.py:140-176) ----
   // WPH warps cooperate on one head (elements strided over them); the three N-reductions go
   // through shared memory in fixed (warp-ascending) order behind a named barrier per head.
-  {
+  if (N == 128 && S <= 7 && p.dbg == nullptr && H <= NWARP && (p.dsw & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
+    // N = 128 (the tracker shapes): one warp per head keeps the head's 128 entries in registers -- lane L holds
+    // n = 4L .. 4L+3 -- from the similarity to the final weighting; the circular shift takes the neighbour lanes'
+    // entries by shuffle.  No shared-memory round trips, no named barriers between the sweeps.
+    if (warp < H) {
+      const int h = warp;
+      const float gate = sG[h], gamma = sGam[h];
+      float kn = 0.0f;                                  // |k_h|^2, fixed summation order
+      for (int w2 = 0; w2 < NWARP; ++w2) kn += sPart[w2 * H + h];
+      const float scale = sBeta[h] * (1.0f / sqrtf(fmaxf(kn, 1e-12f)));   // beta / |k|  (ops.py:152, ntm_cell.py:142)
+      const float4 s4 = *reinterpret_cast<const float4*>(simA + h * Npad + 4 * lane);
+      const float4 p4 = *reinterpret_cast<const float4*>(wprev + h * Npad + 4 * lane);
+      const float x[4] = {s4.x * scale, s4.y * scale, s4.z * scale, s4.w * scale};
+      const float mx = warp_max(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
+      float e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = exp_f(x[u] - mx);
+      const float sum = warp_sum((e[0] + e[1]) + (e[2] + e[3]));
+      const float gs = gate / sum, g1 = 1.0f - gate;    // w_g = g * softmax + (1 - g) * w_prev
+      float win[12];                                     // gated weights of lanes L-1, L, L+1 (circular)
+      win[4] = fmaf(e[0], gs, p4.x * g1); win[5] = fmaf(e[1], gs, p4.y * g1);
+      win[6] = fmaf(e[2], gs, p4.z * g1); win[7] = fmaf(e[3], gs, p4.w * g1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        win[u] = __shfl_sync(0xffffffffu, win[4 + u], (lane + 31) & 31);
+        win[8 + u] = __shfl_sync(0xffffffffu, win[4 + u], (lane + 1) & 31);
+      }
+      float pw[4];
+      auto shift_pow = [&](auto s_tag) {     // circular_shift(x, j)[n] = x[(n + j) mod N], taps j = shift0 .. shift0+S-1
+        constexpr int SS = decltype(s_tag)::value, SH0 = -((SS + 1) / 2);
+        float swv[SS];
+#pragma unroll
+        for (int s2 = 0; s2 < SS; ++s2) swv[s2] = sSw[h * SMAX + s2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float conv = 0.0f;
+#pragma unroll
+          for (int s2 = 0; s2 < SS; ++s2) conv = fmaf(swv[s2], win[4 + u + SH0 + s2], conv);
+          pw[u] = exp2f(gamma * log2f(conv));   // conv >= 0, gamma >= 1: == pow(conv, gamma), 0 -> 0
+        }
+      };
+      if (S == 3) shift_pow(std::integral_constant<int, 3>{});
+      else if (S == 1) shift_pow(std::integral_constant<int, 1>{});
+      else if (S == 5) shift_pow(std::integral_constant<int, 5>{});
+      else shift_pow(std::integral_constant<int, 7>{});
+      const float psum = warp_sum((pw[0] + pw[1]) + (pw[2] + pw[3]));
+      const float rden = 1.0f / (psum + 1e-3f);   // ntm_cell.py:175-176
+      const float4 wv = make_float4(pw[0] * rden, pw[1] * rden, pw[2] * rden, pw[3] * rden);
+      *reinterpret_cast<float4*>(wnew + h * Npad + 4 * lane) = wv;
+      if (last && crank == 0) *reinterpret_cast<float4*>(p.dw + (size_t)bglob * p.dsw + h * N + 4 * lane) = wv;
+    }
+  } else {
     constexpr int WPH = (NWARP / H) > 0 ? (NWARP / H) : 1;
     const int hgrp = warp / WPH, sub = warp - hgrp * WPH;
     const bool multi = (NWARP / H) > 0;                       // else: one warp walks the heads
