@@ -532,3 +532,26 @@ def test_helper_clusters_match_reference_golden(golden_dir, name, gemm_path):
     assert maxerr(to_np(st["read"]), z["final_read"]) <= TOL
     assert maxerr(to_np(st["controller_state"]), z["final_controller_state"]) <= TOL
     assert maxerr(to_np(st["M"])[:, ::sub, ::sub], z["final_M"]) <= TOL
+
+
+@pytest.mark.parametrize("sr,W,R,wf", [(0, 1, 1, False), (1, 1, 4, False), (2, 2, 2, True), (3, 1, 3, False), (3, 3, 4, True)])
+def test_n128_register_addressing_variants(sr, W, R, wf, gemm_path):
+    """N = 128 takes the register-resident addressing path in both the streaming memory kernel and the persistent
+    kernel (one warp per head, the circular shift by lane shuffles, compile-time tap counts 1 / 3 / 5 / 7): every
+    shift range it covers, 1-3 write heads, write_first, against the fp64 oracle."""
+    s = O.NTMShape(output_dim=3, input_dim=20, mem_size=128, mem_dim=64, shift_range=sr, controller_hidden_size=24,
+                   controller_num_layers=1, write_head_size=W, read_head_size=R, write_first=wf)
+    params = O.init_params(s, 11 + sr, 0.3, random_biases=True)      # large weights: peaky softmaxes and sharpening
+    B, T = 7, 6
+    x = np.random.RandomState(3 + sr).standard_normal((B, T, s.input_dim)).astype(np.float32)
+    trk = make_tracker(s, params, T)
+    out, logits = trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    _, rl, rst = O.run_sequence(params, s, x)
+    st = trk.final_state
+    assert maxerr(to_np(logits), rl) <= TOL
+    assert maxerr(to_np(st["w"]), rst["w"]) <= TOL
+    assert maxerr(to_np(st["read"]), rst["read"]) <= TOL
+    assert maxerr(to_np(st["M"]), rst["M"]) <= TOL
+    w = to_np(st["w"])
+    assert (w >= 0).all() and (w.sum(-1) < 1.0 + 1e-5).all()
