@@ -1465,12 +1465,19 @@ int tma_cpl(int H, int MC) {
 
 // Development only (NTM_B200_EXP bit 8): per-CTA timestamps of the last controller / head-parameter GEMM launch of a
 // call, printed to stderr at the end of the call (synchronises the stream).
-long long* g_gemm_prof = nullptr;
+long long* g_gemm_prof_dev[MAX_DEVICES] = {nullptr};     // one buffer per device, allocated on first use, never freed
 long long* gemm_prof_buffer(int which) {
-  if (g_gemm_prof == nullptr && cudaMalloc(&g_gemm_prof, 2 * 256 * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
-  return g_gemm_prof + (size_t)which * 256 * 8;
+  std::lock_guard<std::mutex> lk(config_mutex());
+  long long*& buf = g_gemm_prof_dev[current_device_slot()];
+  if (buf == nullptr && (cudaMalloc(&buf, 2 * 256 * 8 * sizeof(long long)) != cudaSuccess ||
+                         cudaMemset(buf, 0, 2 * 256 * 8 * sizeof(long long)) != cudaSuccess)) {
+    buf = nullptr;
+    return nullptr;
+  }
+  return buf + (size_t)which * 256 * 8;
 }
 void gemm_prof_dump(cudaStream_t stream) {
+  long long* g_gemm_prof = gemm_prof_buffer(0);
   if (g_gemm_prof == nullptr || cudaStreamSynchronize(stream) != cudaSuccess) return;
   std::vector<long long> h(2 * 256 * 8);
   if (cudaMemcpy(h.data(), g_gemm_prof, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;

@@ -235,6 +235,52 @@ class NTMCell(object):
             strides.append(int(t.stride(0)) if B > 1 else inner[key])
         return _cabi.State(*ptrs, *strides), keep
 
+    def _state_geometry(self, B):
+        H, R, N, M = self.num_heads, self.read_head_size, self.mem_size, self.mem_dim
+        CL2 = 2 * self.controller_hidden_size * self.controller_num_layers
+        inner = {"M": N * M, "w": H * N, "read": R * M, "controller_state": CL2}
+        want = {"M": (B, N, M), "w": (B, H, N), "read": (B, R, M), "controller_state": (B, CL2)}
+        return inner, want
+
+    def _device_state(self, state, want, continuation=False):
+        """The reference takes NumPy state through feed_dict (test_tracker.py:284-299): accept host / NumPy state
+        here too -- the kernels only ever see device pointers."""
+        dev, conv = self.device, {}
+        for k, s in want.items():
+            v = state[k]
+            if not torch.is_tensor(v):
+                v = torch.as_tensor(np.asarray(v))
+            if tuple(v.shape) != s:
+                raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(v.shape), s))
+            if v.device != dev or v.dtype != torch.float32:
+                if continuation:
+                    raise ValueError("continuation needs the previous call's device state, got state['%s'] on %s"
+                                     % (k, v.device))
+                v = v.to(dev, torch.float32)
+            conv[k] = v
+        return conv
+
+    def _output_state(self, state, want, out_state):
+        dev = self.device
+        if out_state is None:
+            return {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in want.items()}
+        for k, s in want.items():
+            v = out_state[k]
+            if tuple(v.shape) != s or v.device != dev or v.dtype != torch.float32 or not v.is_contiguous():
+                raise ValueError("out_state['%s'] must be a dense float32 %s tensor on %s" % (k, s, dev))
+            if v.data_ptr() == state[k].data_ptr():
+                raise ValueError("out_state['%s'] aliases the input state" % k)
+        return {k: out_state[k] for k in want}
+
+    def _packed_weights(self, shp, wts, plan, stream):
+        if self._dirty or self._packed is None:
+            lib = _cabi.load()
+            self._packed = torch.empty(int(plan.packed_bytes), dtype=torch.uint8, device=self.device)
+            _cabi.check(lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), self._packed.data_ptr(),
+                                                  self._packed.numel(), stream), "pack_weights")
+            self._dirty = False
+        return self._packed
+
     # ------------------------------------------------------------------- run --
     def _run(self, inputs, state, steps, history=None, workspace=None, continuation=False, out_state=None):
         """inputs [B, steps, D] float32 CUDA contiguous -> (logits, outputs, new_state, taps).
@@ -265,11 +311,7 @@ class NTMCell(object):
         _cabi.check(lib.ntm_b200_query(C.byref(shp), B, T, C.byref(plan)), "query")
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         wts = self._weights_struct()
-        if self._dirty or self._packed is None:
-            self._packed = torch.empty(int(plan.packed_bytes), dtype=torch.uint8, device=dev)
-            _cabi.check(lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), self._packed.data_ptr(),
-                                                  self._packed.numel(), stream), "pack_weights")
-            self._dirty = False
+        self._packed_weights(shp, wts, plan, stream)
         ws = workspace if workspace is not None else self._ws.get((B, T))
         if ws is None or ws.numel() < plan.workspace_bytes:
             if workspace is not None:
@@ -277,40 +319,14 @@ class NTMCell(object):
             self.finish()                                # the old workspace holds the error flag of earlier calls
             ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
             self._ws = {(B, T): ws}                      # keep only the latest geometry
-        H, R, N, M = self.num_heads, self.read_head_size, self.mem_size, self.mem_dim
-        CL2 = 2 * self.controller_hidden_size * self.controller_num_layers
-        inner = {"M": N * M, "w": H * N, "read": R * M, "controller_state": CL2}
-        want = {"M": (B, N, M), "w": (B, H, N), "read": (B, R, M), "controller_state": (B, CL2)}
-        # the reference takes NumPy state through feed_dict (test_tracker.py:284-299): accept host / NumPy
-        # state here too -- the kernels only ever see device pointers
-        conv = {}
-        for k, s in want.items():
-            v = state[k]
-            if not torch.is_tensor(v):
-                v = torch.as_tensor(np.asarray(v))
-            if tuple(v.shape) != s:
-                raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(v.shape), s))
-            if v.device != dev or v.dtype != torch.float32:
-                if continuation:
-                    raise ValueError("continuation needs the previous call's device state, got state['%s'] on %s"
-                                     % (k, v.device))
-                v = v.to(dev, torch.float32)
-            conv[k] = v
-        state = conv
+        inner, want = self._state_geometry(B)
+        state = self._device_state(state, want, continuation)
         if continuation:
             if self.debug or history is not None or any(not state[k].is_contiguous() for k in want):
                 raise ValueError("continuation needs a dense state and neither debug taps nor history")
             new_state = state
-        elif out_state is not None:
-            for k, s in want.items():
-                v = out_state[k]
-                if tuple(v.shape) != s or v.device != dev or v.dtype != torch.float32 or not v.is_contiguous():
-                    raise ValueError("out_state['%s'] must be a dense float32 %s tensor on %s" % (k, s, dev))
-                if v.data_ptr() == state[k].data_ptr():
-                    raise ValueError("out_state['%s'] aliases the input state" % k)
-            new_state = {k: out_state[k] for k in want}
         else:
-            new_state = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in want.items()}
+            new_state = self._output_state(state, want, out_state)
         sin, keep_in = self._state_struct(state, inner)
         sout, keep_out = self._state_struct(new_state, inner)
         logits = torch.empty(B, T, self.output_dim, dtype=torch.float32, device=dev)
@@ -363,11 +379,7 @@ class NTMCell(object):
             _cabi.check(lib.ntm_b200_query(C.byref(shp), B, T, C.byref(plan)), "query")
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             wts = self._weights_struct()
-            if self._dirty or self._packed is None:
-                self._packed = torch.empty(int(plan.packed_bytes), dtype=torch.uint8, device=dev)
-                _cabi.check(lib.ntm_b200_pack_weights(C.byref(shp), C.byref(wts), self._packed.data_ptr(),
-                                                      self._packed.numel(), stream), "pack_weights")
-                self._dirty = False
+            self._packed_weights(shp, wts, plan, stream)
             need = int(lib.ntm_b200_features_workspace_bytes(C.byref(shp), B, L, F))
             if need < 0:
                 raise ValueError("bad shape for the feature-layout call")
@@ -376,28 +388,9 @@ class NTMCell(object):
                 self.finish()
                 ws = torch.empty(need, dtype=torch.uint8, device=dev)
                 self._ws = {("features", B, L, F): ws}
-            H, R, N, M = self.num_heads, self.read_head_size, self.mem_size, self.mem_dim
-            CL2 = 2 * self.controller_hidden_size * self.controller_num_layers
-            inner = {"M": N * M, "w": H * N, "read": R * M, "controller_state": CL2}
-            want = {"M": (B, N, M), "w": (B, H, N), "read": (B, R, M), "controller_state": (B, CL2)}
-            conv = {}
-            for k, sshape in want.items():
-                v = state[k]
-                if not torch.is_tensor(v):
-                    v = torch.as_tensor(np.asarray(v))
-                if tuple(v.shape) != sshape:
-                    raise ValueError("state['%s'] has shape %s, expected %s" % (k, tuple(v.shape), sshape))
-                conv[k] = v.to(dev, torch.float32)
-            if out_state is not None:
-                for k, sshape in want.items():
-                    v = out_state[k]
-                    if tuple(v.shape) != sshape or v.device != dev or v.dtype != torch.float32 or not v.is_contiguous() \
-                            or v.data_ptr() == conv[k].data_ptr():
-                        raise ValueError("out_state['%s'] must be a dense float32 %s tensor on %s, distinct from the input"
-                                         % (k, sshape, dev))
-                new_state = {k: out_state[k] for k in want}
-            else:
-                new_state = {k: torch.empty(sshape, dtype=torch.float32, device=dev) for k, sshape in want.items()}
+            inner, want = self._state_geometry(B)
+            conv = self._device_state(state, want)
+            new_state = self._output_state(conv, want, out_state)
             sin, keep_in = self._state_struct(conv, inner)
             sout, keep_out = self._state_struct(new_state, inner)
             logits = torch.empty(B, T, self.output_dim, dtype=torch.float32, device=dev)
