@@ -74,6 +74,9 @@ struct MemArgs {
                                              // qps_shift: log2(stage uses per sequence) when that is a power of two, else -1
   int NR;                                    // stages of pass 1 that stay in the ring for pass 2 (NS, or 0 = none)
   int exp;                                   // experiment switches (EnvSwitches::exp)
+  int rot;                                   // compact shared-memory plan (large N): three [H][N] buffers rotate between
+                                             // the roles w_prev / gated / final weighting, quad-slot partials live in the
+                                             // similarity buffer; goes with the 4-stage ring (template flag NS4)
   unsigned qps_magic;                        // ceil(2^32 / uses per sequence): division by multiplication (0 = divide)
   int oWp, oRaw, oCn, oBar, oRing;           // w_prev copy, raw parameter row, column norms, mbarriers, ring (floats)
   int vec_out;                               // read-vector rows are 16-byte aligned
@@ -518,9 +521,12 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 // A template parameter rather than a run-time branch: with both addressing variants in one kernel the code grew from
 // 83 KB to 113 KB and the once-per-sequence phases of the OTHER shapes paid for it in instruction-cache misses
 // (C4, N = 1024: addressing 12 -> 25 us per sequence).
-template <int R, int W, int CPL, bool FULLM, bool N128>
+// NS4: a ring of 4 stages (and pass-1 teams of four warps) instead of 8 -- with MemArgs::rot the kernel then fits two
+// CTAs per SM at N*M*4 = 1 MiB (C4: 110 KB per CTA instead of 174 KB), where a second CTA covers the 12 us addressing
+// phase of the first and 512 sequences take two rounds of 296 CTAs instead of four of 148.
+template <int R, int W, int CPL, bool FULLM, bool N128, bool NS4>
 __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a) {
-  constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32, NS = TMA_NS;
+  constexpr int H = R + W, NT = TMA_NT, NWARP = NT / 32, NS = NS4 ? 4 : TMA_NS;
   extern __shared__ float4 mem_smem4[];
   float* smem = reinterpret_cast<float*>(mem_smem4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   float* eS = smem + a.oE;
   float* aS = smem + a.oA;
   float* simS = smem + a.oSim;
-  float* wg = smem + a.oWg;
+  float* wg = smem + a.oWg;          // (with MemArgs::rot these three change roles from sequence to sequence)
   float* wnew = smem + a.oWn;
   float* wprevS = smem + a.oWp;
   float* raw = smem + a.oRaw;
@@ -590,11 +596,11 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   };
   // head parameters, entering weightings and inverse column norms of sequence si -> shared memory
   const uint32_t par_bytes = (uint32_t)(a.PO4 + H * N + M4) * 4u;
-  auto issue_params = [&](int si) {
+  auto issue_params = [&](int si, float* wdst) {
     const size_t bb = (size_t)(blockIdx.x + si * G);
     mbar_expect_tx(parbar, par_bytes);
     bulk_load(raw, a.mc + bb * a.PO4, (uint32_t)a.PO4 * 4u, parbar, pol_drop, hint);
-    bulk_load(wprevS, a.w_in + bb * a.sw_in, (uint32_t)(H * N) * 4u, parbar, pol_drop, hint);
+    bulk_load(wdst, a.w_in + bb * a.sw_in, (uint32_t)(H * N) * 4u, parbar, pol_drop, hint);
     bulk_load(cnS, a.cn + bb * M4, (uint32_t)M4 * 4u, parbar, pol_drop, hint);
   };
 
@@ -607,7 +613,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
   pdl_trigger();
   pdl_wait();                 // head parameters, memories, weightings: all written by earlier kernels of the chain
   if (tid == 0 && nseq > 0) {
-    issue_params(0);
+    issue_params(0, wprevS);
     for (int Qg = 0; Qg < NS && Qg < QT; ++Qg) issue_load(Qg);
   }
 
@@ -621,6 +627,12 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     const int b = blockIdx.x + si * G;
     const int Qb = si * QPS;
     float* Mo = a.Mout + (size_t)b * a.sMout;
+    if (a.rot) {      // sequence si: w_prev arrived in X (even) / Z (odd); gated weights go to the other, the final
+      float* bufX = smem + a.oWp, *bufZ = smem + a.oWg;   // weighting overwrites w_prev head by head
+      wprevS = (si & 1) ? bufZ : bufX;
+      wg = (si & 1) ? bufX : bufZ;
+      wnew = wprevS;
+    }
     MEM_PROF(0);
     mbar_wait_(parbar, (uint32_t)si & 1u);
     MEM_PROF(1);
@@ -701,8 +713,9 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
       // on the current one (a warp only ever waits on the use that directly follows the one it consumed in
       // that slot -- an mbarrier cannot be waited on two phases ahead).  Within a quad of four rows the two
       // members take two rows each.
-      constexpr int NTEAM = NS / 2, WPT = NWARP / NTEAM;
-      static_assert(WPT == 2, "two warps per team");
+      constexpr int NTEAM = NS / 2, WPT = NWARP / NTEAM;      // 4 teams of 2 warps, or (NS4) 2 teams of 4
+      static_assert(WPT == 2 || WPT == 4, "two or four warps per team");
+      constexpr int RBT = 2 * WPT;                            // rows a team takes per sweep step, two per member
       const int team = warp % NTEAM, member = warp / NTEAM;
       const int rv = (lane & 15) / H, hv = (lane & 15) - rv * H;      // reduced value index -> (row of the pair, head)
       for (int q = team; q < NCH; q += NTEAM) {
@@ -710,7 +723,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         mbar_wait_(bars + (Qg & (NS - 1)), (uint32_t)(Qg / NS) & 1u);
         const float* sp = ring + (Qg & (NS - 1)) * stage_floats + 4 * lane + 2 * member * M;
         float* simq = simS + hv * Npad + q * RPS + 2 * member + rv;
-        for (int g0 = 0; g0 < RPS; g0 += RB, sp += RB * M) {
+        for (int g0 = 0; g0 < RPS; g0 += RBT, sp += RBT * M) {
           float acc[2][H];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
@@ -947,7 +960,9 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     __syncthreads();
     MEM_PROF(4);
     // raw / wprevS / cnS are dead now: the next sequence's parameters stream in behind pass 2
-    if (tid == 0 && si + 1 < nseq) issue_params(si + 1);
+    // (rot: the next sequence's weightings land in the gated-weights buffer, dead since the barrier above; the
+    // entering weightings' own buffer holds the final weighting now and is read all through pass 2)
+    if (tid == 0 && si + 1 < nseq) issue_params(si + 1, a.rot ? wg : wprevS);
 
     // ---- pass 2: thread -> (16-byte column chunk c, quad slot rp); per iteration the CTA reads RP quads
     //      of four consecutive rows (= two whole stages) from the ring and writes M' straight to HBM ----
@@ -1038,7 +1053,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
     // ---- finalize: quad slots rp >= 1 park their partials in the (dead) key buffer; slot 0 adds them in
     //      fixed order and writes the read vector and the new inverse column norms ----
     {
-      float* xch = kS;     // [RP-1][R+1][M4]
+      float* xch = a.rot ? simS : kS;     // [RP-1][R+1][M4] (rot: the similarity buffer, dead since the addressing)
       if (worker && rp > 0) {
         float* xw = xch + (rp - 1) * (R + 1) * M4 + 4 * c;
 #pragma unroll
@@ -1378,7 +1393,7 @@ cudaError_t launch_mem(int R, int W, const MemArgs& a, long long B, int smem, cu
 }
 
 // ---- TMA-ring kernel dispatch ----
-template <int R, int W, int CPL, bool FULLM, bool N128>
+template <int R, int W, int CPL, bool FULLM, bool N128, bool NS4>
 cudaError_t launch_tma_v2(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
   if constexpr ((R + W) * CPL > 20) {
     return cudaErrorInvalidValue;
@@ -1390,10 +1405,10 @@ cudaError_t launch_tma_v2(const MemArgs& a, long long B, int smem, cudaStream_t 
       std::lock_guard<std::mutex> lk(config_mutex());
       const int dev = current_device_slot();
       if (configured[dev] != smem) {
-        cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM, N128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(mem_step_tma_kernel<R, W, CPL, FULLM, N128, NS4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured[dev] = smem;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs[dev], mem_step_tma_kernel<R, W, CPL, FULLM, N128>, TMA_NT, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs[dev], mem_step_tma_kernel<R, W, CPL, FULLM, N128, NS4>, TMA_NT, smem);
         if (occs[dev] < 1) occs[dev] = 1;
         int rdev = 0;
         sms[dev] = B200_SMS;
@@ -1406,14 +1421,19 @@ cudaError_t launch_tma_v2(const MemArgs& a, long long B, int smem, cudaStream_t 
     if (g_env_mem_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, g_env_mem_ctas_per_sm));
     long long grid = std::min<long long>(B, (long long)per_sm * nsm);   // persistent CTAs
     if (g_env_mem_grid > 0) grid = std::min<long long>(grid, g_env_mem_grid);
-    return launch_chain(mem_step_tma_kernel<R, W, CPL, FULLM, N128>, (unsigned)grid, TMA_NT, (size_t)smem, stream, g_chain_pdl, a);
+    return launch_chain(mem_step_tma_kernel<R, W, CPL, FULLM, N128, NS4>, (unsigned)grid, TMA_NT, (size_t)smem, stream, g_chain_pdl, a);
   }
 }
 template <int R, int W, int CPL, bool FULLM>
 cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
   const bool n128 = a.N == 128 && a.S <= 7 && (R + W) <= TMA_NT / 32 && (a.sw_out & 3) == 0 &&
-                    (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0;
-  return n128 ? launch_tma_v2<R, W, CPL, FULLM, true>(a, B, smem, stream) : launch_tma_v2<R, W, CPL, FULLM, false>(a, B, smem, stream);
+                    (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0 && a.NS == TMA_NS;
+  if (n128) return launch_tma_v2<R, W, CPL, FULLM, true, false>(a, B, smem, stream);
+  if constexpr (CPL <= 2 && FULLM) {      // the 4-stage ring exists for M = 128 / 256 only (stages of >= 8 rows)
+    if (a.NS == 4) return launch_tma_v2<R, W, CPL, FULLM, false, true>(a, B, smem, stream);
+  }
+  if (a.NS != TMA_NS) return cudaErrorInvalidValue;
+  return launch_tma_v2<R, W, CPL, FULLM, false, false>(a, B, smem, stream);
 }
 template <int R, int W>
 cudaError_t launch_tma_rw(int CPL, const MemArgs& a, long long B, int smem, cudaStream_t stream) {
@@ -1820,6 +1840,34 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
       ma.oRing = o2;
       o2 += ma.NS * ma.RPS * M;
       smem_tma = 4 * o2;
+      // Large N (C4: N = 1024): that plan allows one CTA per SM only.  The compact plan -- 4 ring stages, three
+      // rotating [H][N] buffers instead of four, quad-slot partials in the similarity buffer -- fits two.
+      const int per_cta_2 = (B200_SMEM_SM - 2 * 1024) / 2;
+      const bool full_m = (M == 128 * cpl);
+      if (smem_tma > per_cta_2 && cpl <= 2 && full_m && ma.RPS >= 8 && ma.NCH >= 4 && N != 128 &&
+          (ma.RP - 1) * (R + 1) * M4 <= H * Npad && !(env.exp & 2048)) {
+        int o3 = 0;
+        auto take3 = [&](int n) { int r = o3; o3 += round_up(n, 4); return r; };
+        MemArgs mb = ma;
+        mb.oK = take3(H * M4);
+        mb.oE = take3(W * M4); mb.oA = take3(W * M4);
+        mb.oSim = take3(H * Npad); mb.oWg = take3(H * Npad); mb.oWp = take3(H * Npad); mb.oWn = mb.oWp;
+        mb.oRaw = take3(PO4); mb.oCn = take3(M4);
+        mb.oSm = take3(4 * H + H * SMAX + (TMA_NT / 32) * H + 3 * H * std::max(1, (TMA_NT / 32) / H) + 8);
+        mb.NS = 4; mb.rot = 1;
+        mb.NR = (mb.NCH >= mb.NS && !(env.exp & 2)) ? mb.NS : 0;
+        const int qps2 = 2 * mb.NCH - mb.NR;
+        mb.qps_shift = -1;
+        for (int sh = 0; sh < 30; ++sh)
+          if ((1 << sh) == qps2) mb.qps_shift = sh;
+        mb.qps_magic = 0u;
+        if ((B + 1) * (long long)qps2 * qps2 < (1ll << 32)) mb.qps_magic = (unsigned)(((1ull << 32) + qps2 - 1) / qps2);
+        mb.oBar = take3(2 * (mb.NS + 1) + 2);
+        o3 = round_up(o3, 32);
+        mb.oRing = o3;
+        o3 += mb.NS * mb.RPS * M;
+        if (4 * o3 <= per_cta_2) { ma = mb; smem_tma = 4 * o3; }
+      }
     }
     ma.N = N; ma.M = M; ma.M4 = M4; ma.MC = MC; ma.Npad = Npad; ma.S = S;
     ma.shift0 = -((S + 1) / 2);   // Python-2 floor(-S/2), ops.py:204
