@@ -74,6 +74,7 @@ struct MemArgs {
                                              // qps_shift: log2(stage uses per sequence) when that is a power of two, else -1
   int NR;                                    // stages of pass 1 that stay in the ring for pass 2 (NS, or 0 = none)
   int exp;                                   // experiment switches (EnvSwitches::exp)
+  int P2S;                                   // pass 2: stage pairs (iterations) per CTA barrier / re-issue round, 1 or 2
   int rot;                                   // compact shared-memory plan (large N): three [H][N] buffers rotate between
                                              // the roles w_prev / gated / final weighting, quad-slot partials live in the
                                              // similarity buffer; goes with the 4-stage ring (template flag NS4)
@@ -774,6 +775,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
         // (the last NR stages stay where they are for pass 2)
         if (q < NCH - NR) {
           asm volatile("bar.sync %0, %1;" ::"r"(8 + team), "r"(32 * WPT) : "memory");
+          // (rotating the issuing member over the team's warps changes nothing: measured)
           if (member == 0 && lane == 0 && Qg + NS < QT) issue_load(Qg + NS);
         }
       }
@@ -981,7 +983,11 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
       const int qps = RP >> 1;                     // quads per stage
       const int sk = rp >= qps ? 1 : 0;            // which of the iteration's two stages this thread's quad is in
       const int NIT = N / RS;                      // iterations = NCH / 2
-      for (int it = 0; it < NIT; ++it) {
+      // P2S iterations (stage pairs) share one CTA barrier and one round of re-issues: every bulk copy costs its
+      // issuing warp ~240 ns right behind the barrier, i.e. on the whole CTA's critical path
+      const int P2S = a.P2S;
+      for (int it0 = 0; it0 < NIT; it0 += P2S) {
+       for (int it = it0; it < it0 + P2S; ++it) {
         // position p = 2 * it of pass 2: the stages retained from pass 1 first (rows from stage NCH - NR on), then
         // the re-read stages 0 .. NCH-NR-1
         const int nb = (2 * it < NR ? (NCH - NR + 2 * it) : (2 * it - NR)) * RPS;
@@ -1039,11 +1045,13 @@ __global__ void __launch_bounds__(TMA_NT, 2) mem_step_tma_kernel(const MemArgs a
           };
           if (a.write_first) quad(std::true_type{}); else quad(std::false_type{});
         }
-        __syncthreads();         // every reader of this iteration's stage is done
-        // one bulk copy costs its issuing thread ~240 ns (tools/tma_probe.cu): rotate the issuer over the
-        // warps so that no warp pays it twice in a row
-        if ((tid & 31) == 0 && ((warp - 2 * it) & (NWARP - 1)) < 2) {   // two issuers, rotating over the warps
-          const int Qn = Qb + NCH - NR + 2 * it + ((warp - 2 * it) & (NWARP - 1)) + NS;
+       }
+        __syncthreads();         // every reader of these stages is done
+        // one bulk copy costs its issuing thread ~240 ns (tools/tma_probe.cu): one issuer per freed slot, in
+        // different warps, rotating over the warps so that no warp pays it twice in a row
+        const int ik = (warp - 2 * it0) & (NWARP - 1);
+        if ((tid & 31) == 0 && ik < 2 * P2S) {
+          const int Qn = Qb + NCH - NR + 2 * it0 + ik + NS;
           if (Qn < QT) issue_load(Qn);
         }
       }
@@ -1869,6 +1877,8 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
         if (4 * o3 <= per_cta_2) { ma = mb; smem_tma = 4 * o3; }
       }
     }
+    ma.P2S = 1;
+    if (cpl && ma.NS == TMA_NS && ma.RP > 0 && (N / (4 * ma.RP)) % 2 == 0 && ma.NR % 4 == 0 && !(env.exp & 4096)) ma.P2S = 2;
     ma.N = N; ma.M = M; ma.M4 = M4; ma.MC = MC; ma.Npad = Npad; ma.S = S;
     ma.shift0 = -((S + 1) / 2);   // Python-2 floor(-S/2), ops.py:204
     ma.P = P; ma.PO4 = PO4; ma.O = s->output_dim; ma.write_first = s->write_first ? 1 : 0; ma.T = (int)T;
