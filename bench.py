@@ -19,6 +19,7 @@ pinned HOST inputs and host results (H2D and D2H inside the timed region).
 run here) on the host cores, on a bounded sample of the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -326,6 +327,11 @@ def measure(workload, ctx, steps, warmup, want_e2e=True, want_clocks=True, batch
     for _ in range(max(warmup, 3)):
         one_step()
     trk.cell.finish()
+    # Python's cyclic collector: a full collection over the interpreter's ~10^6 objects (torch, numpy) costs 20-40 ms
+    # -- a whole C3 pass -- and used to land inside a timed step now and then (one 40.7 ms call among 18.4 ms ones on
+    # 2 GPUs).  Collect now, park what exists in the permanent generation; nothing is disabled.
+    gc.collect()
+    gc.freeze()
 
     # ---------------- device-resident timing: K steps, CUDA events, max over ranks ---------
     # Two back-to-back timed regions of K steps each.  Region 1 is the one `value` comes from: nothing but
