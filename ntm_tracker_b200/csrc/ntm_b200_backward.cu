@@ -374,7 +374,10 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
     cudaEventRecord(g_bev[0], stream);
   }
 
-  // ---- reverse-time loop ----
+  // ---- reverse-time loop: four launches per step, chained by programmatic dependent launch (every kernel waits for
+  //      its predecessor before touching memory; what hides is the launch latency).  Off with per-kernel profiling
+  //      events between the launches and with NTM_B200_EXP bit 16. ----
+  const bool pdl = !prof && !(read_env().exp & 16);
   int cur = 0;
   for (long long t = T - 1; t >= 0; --t) {
     float* draw = DMC + (size_t)t * B * PO4;
@@ -384,13 +387,13 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
                                        dwbuf[cur ^ 1], draw, dlogits, (int)T, (int)t,
                                        (hist->sim && hist->cn) ? hist->sim + (size_t)t * B * H * N : nullptr,
                                        (hist->sim && hist->cn) ? hist->cn + (size_t)t * B * M : nullptr, rowDraw, y.pA.KAtot,
-                                       stream);
+                                       stream, pdl && t < T - 1);
     if (st) return st == NTM_B200_ERR_CUDA ? set_cuda_error_ext(cudaGetLastError(), "mem_backward_kernel") : st;
     if (prof) cudaEventRecord(g_bev[2 + 2 * (T - 1 - t)], stream);
     cur ^= 1;
     // d_h(top) = d_raw @ [W_addr | W_out]^T, K slices into slabs
     // (the memory-backward kernel has already written d_raw into the row-operand tiles)
-    BWD_CK(gemmt::launch(y.pA, rowDraw, colWao, dh, C, B * (long long)C, stream), "gemm_tiles(d_h)");
+    BWD_CK(gemmt::launch(y.pA, rowDraw, colWao, dh, C, B * (long long)C, stream, pdl), "gemm_tiles(d_h)");
     count_launch();
     for (int l = L - 1; l >= 0; --l) {
       const float* dh_b = (l == L - 1) ? dh : dcat[l + 1];
@@ -401,14 +404,15 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
                                        hist->z + ((size_t)t * B * L + l) * 4 * C, (long long)L * 4 * C,
                                        hist->c + ((size_t)t * B * L + l) * C, hist->c + ((size_t)(t + 1) * B * L + l) * C,
                                        (long long)L * C, dc + (size_t)l * B * C, dz, (long long)L * 4 * C, rowDz, y.pB[l].KAtot,
-                                       stream);
+                                       stream, pdl);
       if (st) return set_cuda_error_ext(cudaGetLastError(), "lstm_backward_kernel");
       // d_cat_l = d_z_l @ W_l[off:]^T  -> [d_read | d_h_l] (layer 0) or [d_h_{l-1} (this step) | d_h_l (previous step)]
       if (C % 8 != 0) {     // (else the LSTM backward kernel has written d_z into the row-operand tiles itself)
         BWD_CK(gemmt::pack(dz, (long long)L * 4 * C, 1, 0, 0, (int)B, 4 * C, rowDz, y.pB[l].KAtot, 0, 0, false, nsm, stream), "pack(d_z)");
         count_launch();
       }
-      BWD_CK(gemmt::launch(y.pB[l], rowDz, reinterpret_cast<uint8_t*>(ws + y.off_colWl[l]), dcat[l], y.ncat[l], 0, stream),
+      BWD_CK(gemmt::launch(y.pB[l], rowDz, reinterpret_cast<uint8_t*>(ws + y.off_colWl[l]), dcat[l], y.ncat[l], 0, stream,
+                           pdl && C % 8 == 0),
              "gemm_tiles(d_cat)");
       count_launch();
     }

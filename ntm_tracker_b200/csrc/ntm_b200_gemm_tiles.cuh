@@ -65,6 +65,8 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_tiles_kernel(const Arg
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_trigger();      // (programmatic dependent launch along the reverse-time loop: barrier init and the TMEM
+  pdl_wait();         // allocation above overlap the predecessor's tail; operands and outputs are touched after this)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -189,7 +191,7 @@ inline Plan make_plan(int nrows, int ncols, int K, int kslices_want) {
 inline int smem_bytes() { return 1024 + NSLOT * 2 * REC_BYTES; }
 
 static inline cudaError_t launch(const Plan& p, const uint8_t* rowT, const uint8_t* colT, float* out, int ldo, long long slab,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool pdl = false) {
   Args a{};
   a.rowT = rowT; a.colT = colT; a.out = out; a.slab = slab; a.ldo = ldo; a.nrows = p.nrows; a.ncols = p.ncols;
   a.nrb = p.nrb; a.ncb = p.ncb; a.KAtot = p.KAtot; a.KA = p.KA; a.kslices = p.kslices;
@@ -204,8 +206,7 @@ static inline cudaError_t launch(const Plan& p, const uint8_t* rowT, const uint8
       configured[dev] = smem;
     }
   }
-  gemm_tiles_kernel<<<p.nrb * p.ncb * p.kslices, THREADS, smem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_chain(gemm_tiles_kernel, (unsigned)(p.nrb * p.ncb * p.kslices), (unsigned)THREADS, (size_t)smem, stream, pdl, a);
 }
 
 static inline cudaError_t pack(const float* src, long long si, long long sk, int pB, int pT, int nI, int nK, uint8_t* tiles,

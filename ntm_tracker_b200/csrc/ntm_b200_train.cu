@@ -129,6 +129,8 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // lane, combined by one transposing reduction per quad).  Two CTAs per SM.
 template <int R, int W, bool VEC>
 __global__ void __launch_bounds__(NT, 2) mem_backward_kernel(const BwdParams q) {
+  pdl_trigger();      // reverse-time loop chained by programmatic dependent launch: the launch latency of the next
+  pdl_wait();         // kernel hides behind this one; nothing is touched before the predecessor has completed
   constexpr int H = R + W;
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -619,6 +621,8 @@ __global__ void __launch_bounds__(256) lstm_backward_kernel(int B, int C, const 
                                      const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                      long long c_stride, float* __restrict__ dc, float* __restrict__ dz,
                                      long long dz_stride, uint8_t* tiles, int KAtot) {
+  pdl_trigger();
+  pdl_wait();
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i0 < (long long)B * C;
   const long long i = live ? i0 : 0;            // tail lanes recompute element 0 and store nothing
@@ -671,7 +675,7 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
                            const float* raw_params, const float* d_read, long long sdr, const float* d_w, float* dM,
                            float* d_w_prev, float* d_raw_params, const float* dlogits, int T, int t,
                            const float* sim_hist, const float* cn_hist, uint8_t* tiles_raw, int KAtot_raw,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, bool pdl) {
   BwdParams q{};
   q.sim_hist = sim_hist; q.cn_hist = cn_hist; q.tiles_raw = tiles_raw; q.KAtot_raw = KAtot_raw;
   const int R = s->read_head_size, W = s->write_head_size, H = R + W;
@@ -705,22 +709,22 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
     cudaGetLastError();
     return NTM_B200_ERR_CUDA;
   }
-  k<<<(unsigned)batch, NT, smem, stream>>>(q);
+  const cudaError_t le = launch_chain(k, (unsigned)batch, (unsigned)NT, (size_t)smem, stream, pdl, q);
   count_launch();
-  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+  return le == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
 }
 
 int launch_lstm_backward(long long batch, int hidden, const float* dh_a, long long lda, const float* dh_b, long long ldb,
                          int nslab, long long slab, const float* z, long long z_stride, const float* c_prev,
                          const float* c_new, long long c_stride, float* dc, float* dz, long long dz_stride,
-                         uint8_t* tiles, int KAtot, cudaStream_t stream) {
+                         uint8_t* tiles, int KAtot, cudaStream_t stream, bool pdl) {
   const long long total = batch * hidden;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (hidden % 8 != 0) tiles = nullptr;      // the caller packs d_z with the generic kernel instead
-  lstm_backward_kernel<<<blocks, 256, 0, stream>>>((int)batch, hidden, dh_a, lda, dh_b, ldb, nslab, slab, z, z_stride,
-                                                  c_prev, c_new, c_stride, dc, dz, dz_stride, tiles, KAtot);
+  const cudaError_t le = launch_chain(lstm_backward_kernel, blocks, 256u, (size_t)0, stream, pdl, (int)batch, hidden, dh_a, lda, dh_b,
+                                      ldb, nslab, slab, z, z_stride, c_prev, c_new, c_stride, dc, dz, dz_stride, tiles, KAtot);
   count_launch();
-  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+  return le == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
 }
 
 }  // namespace train

@@ -19,7 +19,7 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
                            const float* raw_params, const float* d_read, long long sdr, const float* d_w, float* dM,
                            float* d_w_prev, float* d_raw_params, const float* dlogits, int T, int t,
                            const float* sim_hist, const float* cn_hist, uint8_t* tiles_raw, int KAtot_raw,
-                           cudaStream_t stream);
+                           cudaStream_t stream, bool pdl = false);
 
 // BasicLSTMCell backward, elementwise part.  dh = dh_a[b*lda + u] (null = 0) + sum over `nslab` K-slice slabs
 // of dh_b[s*slab + b*ldb + u] (null = 0).  tiles (may be null; used when hidden % 8 == 0): operand tile records that
@@ -27,7 +27,7 @@ int launch_memory_backward(const ntm_b200_shape* s, long long batch, const float
 int launch_lstm_backward(long long batch, int hidden, const float* dh_a, long long lda, const float* dh_b, long long ldb,
                          int nslab, long long slab, const float* z, long long z_stride, const float* c_prev,
                          const float* c_new, long long c_stride, float* dc, float* dz, long long dz_stride,
-                         uint8_t* tiles, int KAtot, cudaStream_t stream);
+                         uint8_t* tiles, int KAtot, cudaStream_t stream, bool pdl = false);
 
 }  // namespace train
 }  // namespace ntm_b200
