@@ -66,18 +66,24 @@ __global__ void __launch_bounds__(1024) offset_loss_kernel(const LossArgs a) {
 }
 
 // ------------------------------------------------------------------------------- column sums --
+constexpr int COLSUM_MAX_CHUNKS = 16;
 // dst[j] = f(sum_r src[r * ld + j]), j < ncols: bias gradients (sum over all (t, b)) and the init_state
 // gradients (sum over the batch, times the derivative of the activation the variable goes through:
 // mode 1: s0 = tanh(var) -> (1 - s0^2); mode 2: s0 = sigmoid(var) -> s0 (1 - s0)).  A CTA owns 32 columns;
 // 8 row phases per column, combined in phase order.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, long long ld, long long nrows, int ncols,
-                                                     float* __restrict__ dst, const float* __restrict__ s0, int mode) {
+// Tall matrices (8192 rows x 800 columns would be 25 CTAs): gridDim.y row chunks write partial sums to `scratch`
+// [chunks][ncols] and colsum_final_kernel adds them in chunk order; a single chunk writes dst directly.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, long long ld, long long nrows_all, int ncols,
+                                                     float* __restrict__ dst, const float* __restrict__ s0, int mode,
+                                                     float* __restrict__ scratch, long long rows_per_chunk) {
   __shared__ float part[8][33];
   const int cl = threadIdx.x & 31, ph = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cl;
+  const long long r_begin = (long long)blockIdx.y * rows_per_chunk;
+  const long long nrows = r_begin + rows_per_chunk < nrows_all ? r_begin + rows_per_chunk : nrows_all;
   float acc = 0.0f;
   if (j < ncols) {
-    long long r = ph;
+    long long r = r_begin + ph;
     for (; r + 24 < nrows; r += 32) {      // four independent loads in flight
       const float v0 = __ldg(src + r * ld + j), v1 = __ldg(src + (r + 8) * ld + j);
       const float v2 = __ldg(src + (r + 16) * ld + j), v3 = __ldg(src + (r + 24) * ld + j);
@@ -91,10 +97,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += part[i][cl];
+    if (gridDim.y > 1) { scratch[(size_t)blockIdx.y * ncols + j] = s; return; }
     if (mode == 1) { const float a0 = s0[j]; s *= (1.0f - a0 * a0); }
     else if (mode == 2) { const float a0 = s0[j]; s *= a0 * (1.0f - a0); }
     dst[j] = s;
   }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ scratch, int chunks, int ncols, float* __restrict__ dst,
+                                    const float* __restrict__ s0, int mode) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  float s = 0.0f;
+  for (int c = 0; c < chunks; ++c) s += scratch[(size_t)c * ncols + j];
+  if (mode == 1) { const float a0 = s0[j]; s *= (1.0f - a0 * a0); }
+  else if (mode == 2) { const float a0 = s0[j]; s *= a0 * (1.0f - a0); }
+  dst[j] = s;
 }
 
 // dst[i] = sum over slabs (slice order) of src[s * slab + i]   (split-K partials of a weight-gradient GEMM)
@@ -174,7 +191,8 @@ struct Layout {
   gemmt::Plan pB[MAXL];                       // d_cat_l  = d_z_l [B, 4C]   x  W_l[off:]^T
   gemmt::Plan pGao;                           // d Wao    = hc^T [C, TB]    x  DMC
   gemmt::Plan pGw[MAXL];                      // d W_l    = inp_l^T         x  DZ_l
-  long long off_dM, off_dw[2], off_dc, off_dcat[MAXL], off_dh, off_DMC, off_DZ, off_tmpb, off_slabs;
+  long long off_dM, off_dw[2], off_dc, off_dcat[MAXL], off_dh, off_DMC, off_DZ, off_tmpb, off_slabs, off_colsum;
+  long long colsum_floats;
   long long off_rowDraw, off_colWao, off_rowDz, off_colWl[MAXL], off_rowG, off_colG;
   long long tiles_begin, tiles_end, total;
   long long slabs_floats;
@@ -214,6 +232,8 @@ void make_layout(const ntm_b200_shape* s, long long B, long long T, Layout* y) {
   y->off_DMC = take(4ll * TB * y->PO4);
   y->off_DZ = take(4ll * TB * L * 4 * C);
   y->off_tmpb = take(4ll * y->PO4);
+  y->colsum_floats = (long long)bwd::COLSUM_MAX_CHUNKS * std::max(y->PO4, 4 * C);     // row-chunk partials of the bias sums
+  y->off_colsum = take(4ll * y->colsum_floats);
   long long slabs = (long long)y->pGao.kslices * C * y->PO4;
   for (int l = 0; l < L; ++l) slabs = std::max(slabs, (long long)y->pGw[l].kslices * y->inK[l] * 4 * C);
   y->slabs_floats = slabs;
@@ -242,10 +262,23 @@ void make_layout(const ntm_b200_shape* s, long long B, long long T, Layout* y) {
     if (e_ != cudaSuccess) return set_cuda_error_ext(e_, what);       \
   } while (0)
 
+// scratch (may be null -> one chunk): room for COLSUM_MAX_CHUNKS * ncols floats
 int launch_colsum(const float* src, long long ld, long long nrows, int ncols, float* dst, const float* s0, int mode,
-                  cudaStream_t stream) {
-  colsum_kernel<<<(ncols + 31) / 32, 256, 0, stream>>>(src, ld, nrows, ncols, dst, s0, mode);
+                  cudaStream_t stream, float* scratch = nullptr, long long scratch_floats = 0) {
+  const int cblocks = (ncols + 31) / 32;
+  int chunks = 1;
+  if (scratch != nullptr && cblocks < 2 * B200_SMS) {      // not enough column blocks to fill the device: split the rows
+    chunks = (int)std::min<long long>(COLSUM_MAX_CHUNKS, std::max<long long>(1, nrows / 256));
+    chunks = (int)std::min<long long>(chunks, scratch_floats / std::max(1, ncols));
+    if (chunks < 1) chunks = 1;
+  }
+  const long long rpc = (nrows + chunks - 1) / chunks;
+  colsum_kernel<<<dim3(cblocks, chunks), 256, 0, stream>>>(src, ld, nrows, ncols, dst, s0, mode, scratch, rpc);
   count_launch();
+  if (chunks > 1) {
+    colsum_final_kernel<<<(ncols + 255) / 256, 256, 0, stream>>>(scratch, chunks, ncols, dst, s0, mode);
+    count_launch();
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -430,7 +463,7 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
     BWD_CK(gemmt::pack(DMC, 1, PO4, 0, 0, PO4, (int)TB, colG, y.pGao.KAtot, 0, 0, true, nsm, stream), "pack(d_raw^T)");
     BWD_CK(gemmt::launch(y.pGao, rowG, colG, slabs, PO4, (long long)C * PO4, stream), "gemm_tiles(d Wao)");
     for (int i = 0; i < 3; ++i) count_launch();
-    if (bwd::launch_colsum(DMC, PO4, TB, PO4, tmpb, nullptr, 0, stream)) return set_cuda_error_ext(cudaGetLastError(), "colsum(d_raw)");
+    if (bwd::launch_colsum(DMC, PO4, TB, PO4, tmpb, nullptr, 0, stream, reinterpret_cast<float*>(ws + y.off_colsum), y.colsum_floats)) return set_cuda_error_ext(cudaGetLastError(), "colsum(d_raw)");
     bwd::unpack_ao_grads_kernel<<<eg, eb, 0, stream>>>(slabs, (long long)C * PO4, y.pGao.kslices, tmpb, C, P, O, PO4,
                                                       g->addr_w, g->addr_b, g->out_w, g->out_b);
     count_launch();
@@ -466,7 +499,8 @@ extern "C" int32_t ntm_b200_backward_seq(const ntm_b200_shape* s, const ntm_b200
       count_launch(); count_launch();
       BWD_CK(cudaGetLastError(), "sum_slabs_kernel");
     }
-    if (bwd::launch_colsum(DZ + (size_t)l * 4 * C, (long long)L * 4 * C, TB, 4 * C, g->lstm_b[l], nullptr, 0, stream))
+    if (bwd::launch_colsum(DZ + (size_t)l * 4 * C, (long long)L * 4 * C, TB, 4 * C, g->lstm_b[l], nullptr, 0, stream,
+                           reinterpret_cast<float*>(ws + y.off_colsum), y.colsum_floats))
       return set_cuda_error_ext(cudaGetLastError(), "colsum(d_z)");
   }
   // ---- init_state variables: tiled over the batch, so their gradients are batch sums (ntm_cell.py:292-306) ----
