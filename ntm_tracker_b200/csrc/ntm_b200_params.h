@@ -101,7 +101,17 @@ struct EnvSwitches {
   bool old_gemm;             // NTM_B200_OLD_GEMM
   int mem_ctas_per_sm;       // NTM_B200_MEM_CTAS_PER_SM (0 = occupancy)
   int mem_grid;              // NTM_B200_MEM_GRID: cap on the persistent memory kernel's CTAs (0 = none; experiments)
-  int exp;                   // NTM_B200_EXP: bit mask of experiment switches (development only; 0 in production)
+  int exp;                   // NTM_B200_EXP: bit mask of experiment switches (development only; 0 in production):
+                             //    1  gemm_ws: two bulk-copy issuing lanes per record instead of four
+                             //    2  memory kernel: no pass-1 stages retained in the ring for pass 2
+                             //    4  scalar gate kernel (lstm_stream_kernel) instead of the vectorised one
+                             //    8  gemm_ws in-kernel phase timers, printed to stderr per call (synchronises)
+                             //   16  no programmatic dependent launch (forward chain and reverse-time loop)
+                             //   32  input projection on the tile kernel (ntm_b200_xproj_tc.cuh) in streaming mode too
+                             //   64 / 128  resident mode: helper clusters never / always
+                             //  256  memory kernel: evict-last instead of the normal L2 policy on re-read pass-1 stages
+                             // 2048  memory kernel: no compact shared-memory plan for large N (one CTA per SM at C4)
+                             // 4096  memory kernel pass 2: one stage pair per CTA barrier instead of two
 };
 EnvSwitches read_env();
 
