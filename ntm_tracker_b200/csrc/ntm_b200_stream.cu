@@ -1163,6 +1163,13 @@ __global__ void __launch_bounds__(INIT_NT) init_mem_kernel(const float* __restri
   }
 }
 
+// rows 1 .. B-1 of a [B][n] array := row 0 (the initial memory is one broadcast copy: its column norms are computed once)
+__global__ void bcast_row0_kernel(float* a, int n, long long B) {
+  const long long total = (B - 1) * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    a[n + i] = a[i % n];
+}
+
 struct SmallInitArgs {
   int H, N, R, M, C, L;
   const float *w_in, *read_in, *ctrl_in;
@@ -1755,9 +1762,17 @@ int stream_forward(const ntm_b200_shape* s, const ntm_b200_weights* w, const flo
   // zero_state broadcasts it, stride 0) and writes the working memory; only its column norms are derived here.
   const bool lazy_M0 = !hM;
   if (!cont) {
-    init_mem_kernel<<<(unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(in->M, in->stride_M, lazy_M0 ? const_cast<float*>(in->M) : M0,
-                                                                    lazy_M0 ? in->stride_M : sM0, cn, N, M, M4, MC, WPCi);
+    // zero_state hands ONE copy of the initial memory to all sequences (batch stride 0): without a history nothing is
+    // copied, so one CTA derives the column norms and a second kernel replicates the row (4096 CTAs re-reading the
+    // same 256 KiB cost 0.09-0.18 ms per call)
+    const bool one_copy = lazy_M0 && in->stride_M == 0 && B > 1;
+    init_mem_kernel<<<one_copy ? 1u : (unsigned)B, INIT_NT, WPCi * M4 * 4, stream>>>(
+        in->M, in->stride_M, lazy_M0 ? const_cast<float*>(in->M) : M0, lazy_M0 ? in->stride_M : sM0, cn, N, M, M4, MC, WPCi);
     count_launch();
+    if (one_copy) {
+      bcast_row0_kernel<<<nsm, 256, 0, stream>>>(cn, M4, B);
+      count_launch();
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return set_cuda_error_ext(e, "init_mem_kernel");
   }
   if (!cont) {
