@@ -376,8 +376,12 @@ int choose_mode(const ntm_b200_shape* s, const HostPlan& hp, long long B, bool d
   if (debug_taps || !stream_supported(s, nsm)) return 0;
   if (env.mode >= 0) return env.mode;
   // resident: ceil(B / G) waves of ~30 us steps; streaming pays ~4 launches + GEMM weight loads per step
-  // but its step time grows only with the HBM traffic.  Measured crossover (profiles/): a few waves.
-  long long thr = 3ll * hp.Gteam_max * hp.max_teams;
+  // but its step time grows only with the HBM traffic.  Measured crossover at tracker shapes, T = 16
+  // (profiles/r2_ab_probes.txt): with the round-2 streaming path (programmatic dependent launch, faster GEMM
+  // issue / prologue) streaming wins as soon as the batch needs a second wave -- B = 74: 1.72 vs 1.19 M seq-steps/s,
+  // 111: 1.45 vs 1.79, 148: 1.91 vs 2.30, 222: 1.96 vs 3.31 (round 1: three waves).  Shapes that run the fallback
+  // streaming kernels keep the older threshold.
+  long long thr = (stream_ws_path(s) ? 1ll : 3ll) * hp.Gteam_max * hp.max_teams;
   if (env.stream_min_batch >= 0) thr = env.stream_min_batch;
   return B > thr ? 1 : 0;
 }

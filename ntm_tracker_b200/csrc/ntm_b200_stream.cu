@@ -1565,6 +1565,13 @@ bool stream_supported(const ntm_b200_shape* s, int nsm) {
 // The hoisted input projection runs on the warp-specialised GEMM when the controller is single-layer with the
 // operand-tile path (as stream_forward decides), and the input width is a whole number of 64-wide K atoms (at most
 // KA_MAX of them) plus at most 8 columns (the tracker's 512 features + delimiter + target channels).
+// true when the per-timestep chain runs on the warp-specialised GEMMs and the TMA-ring memory kernel (what
+// stream_forward's `use_ws` decides): the fast streaming path the mode choice's crossover was measured on
+bool stream_ws_path(const ntm_b200_shape* s) {
+  const int C = s->controller_hidden_size, H = s->read_head_size + s->write_head_size, M = s->mem_dim;
+  return s->controller_num_layers == 1 && M % 8 == 0 && C % 8 == 0 && tma_rps(s->mem_size, M) > 0 && tma_cpl(H, M / 4) > 0;
+}
+
 static bool xproj_ws_shape(const ntm_b200_shape* s, int* xK, int* xrem) {
   const int C = s->controller_hidden_size, H = s->read_head_size + s->write_head_size, M = s->mem_dim, D = s->input_dim;
   if (s->controller_num_layers != 1 || M % 8 != 0 || C % 8 != 0 || M % 4 != 0) return false;

@@ -27,6 +27,7 @@ struct StreamWorkspace {
 
 // true when the shape is one the streaming kernels cover (M % 4 == 0, GEMM widths within the tile kernel)
 bool stream_supported(const ntm_b200_shape* s, int nsm);
+bool stream_ws_path(const ntm_b200_shape* s);   // the chain runs on gemm_ws_kernel + mem_step_tma_kernel
 void stream_layout(const ntm_b200_shape* s, long long B, long long T, StreamWorkspace* ws);
 
 // Runs T steps for B sequences.  xw = hoisted x-projection [B,T,4C] (already computed on `stream`),

@@ -193,7 +193,10 @@ def test_execution_mode_choice(lib, monkeypatch):
         return m.value
 
     assert mode(shape(), 64) == 0            # BASELINE config 2: one wave of 74 resident sequences
-    assert mode(shape(), 222) == 0           # three waves
+    assert mode(shape(), 74) == 0            # exactly one wave
+    assert mode(shape(), 111) == 1           # a second wave: streaming wins from here on (measured, round 2)
+    assert mode(shape(controller_num_layers=2), 222) == 0        # fallback streaming kernels: three waves as before
+    assert mode(shape(controller_num_layers=2), 223) == 1
     assert mode(shape(), 256) == 1           # BASELINE config 5 (per GPU)
     assert mode(shape(), 4096) == 1          # BASELINE config 3
     assert mode(shape(mem_size=1024, mem_dim=256), 512) == 1     # BASELINE config 4
