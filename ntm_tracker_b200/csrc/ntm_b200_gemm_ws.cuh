@@ -194,20 +194,24 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
     const int jcol = tile * 128 + jl;
     // weight hi half -> TMEM (once)
     {
-      // 16 k = 8 packed words per step; four steps' loads are issued together (the staging is a chain of L2
-      // round trips otherwise, and at small batches it is most of the kernel)
+      // 16 k = 8 packed words per step; SB steps' loads are issued together (the staging is a chain of L2 round
+      // trips otherwise, and at small batches it is most of the kernel; 8 or 16 steps per batch measure the same 4.5 us)
+#ifndef NTM_STAGE_SB
+#define NTM_STAGE_SB 4
+#endif
+      constexpr int SB = NTM_STAGE_SB;
       auto stage_weights = [&](const uint32_t* src, uint32_t tdst) {   // src: this lane's 8 words of 16-k step 0
         const int nq = nka * 4;
-        for (int q0 = 4 * chalf; q0 < nq; q0 += 8) {    // the quarter's two warps alternate blocks of four steps
-          uint4 w4[8];
+        for (int q0 = SB * chalf; q0 < nq; q0 += 2 * SB) {    // the quarter's two warps alternate blocks of SB steps
+          uint4 w4[2 * SB];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < SB; ++i) {
             const int q = min(q0 + i, nq - 1);
             w4[2 * i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * 1024));
             w4[2 * i + 1] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)q * 1024 + 4));
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < SB; ++i) {
             if (q0 + i < nq) {
               const uint32_t v[8] = {w4[2 * i].x, w4[2 * i].y, w4[2 * i].z, w4[2 * i].w,
                                      w4[2 * i + 1].x, w4[2 * i + 1].y, w4[2 * i + 1].z, w4[2 * i + 1].w};
