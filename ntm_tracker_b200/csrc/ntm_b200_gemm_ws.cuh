@@ -107,9 +107,9 @@ static __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const Args a
 
   if (warp == 0) {
     // ------------------------------------------------ producer ------------------------------------
-    if (lane == 0 && !a.wlo_tmem) {
-      mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
-      for (int k = 0; k < nka; ++k)
+    if (!a.wlo_tmem) {      // weight lo half: one 16 KiB bulk copy per K atom, each from its own lane (~240 ns per issue)
+      if (lane == 0) mbar_expect_tx(&wbar, (uint32_t)nka * ATOM_BYTES);
+      for (int k = lane; k < nka; k += 32)
         bulk_g2s(sWlo + (size_t)k * ATOM_BYTES, a.wlo + (wrec * a.KA + k) * ATOM_BYTES, ATOM_BYTES, &wbar);
     }
     // Two issuing lanes: lane 0 brings the hi half of a record, lane 1 the lo half (a bulk copy costs its
