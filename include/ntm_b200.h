@@ -215,6 +215,13 @@ int32_t ntm_b200_serialize_tracker_inputs(const float* features, const float* ta
 int32_t ntm_b200_gather_offsets(const float* logits, float* offsets, int64_t batch, int32_t frames,
                                 int32_t num_features, int32_t output_dim, void* stream);
 
+/* NTMCell.zero_state (ntm_cell.py:284-315): the initial memory / weightings / read vectors of every sequence are
+ * tanh / sigmoid / tanh of the three init_state variables (the weighting is NOT normalised: reference quirk 4).
+ * One launch over the three arrays ([N,M], [H,N], [R,M] floats); the batch dimension is a stride-0 broadcast on
+ * the caller's side. */
+int32_t ntm_b200_zero_state(const float* var_M, int64_t n_M, const float* var_w, int64_t n_w, const float* var_read,
+                            int64_t n_read, float* M, float* w, float* read, void* stream);
+
 /* ntm_b200_forward_seq for frames in FEATURE layout: conv features [B, L, F, Cch] + first-frame target map [B, F]
  * (what direct_offset_output.py:439-500 concatenates / tiles / reshapes into the tracker inputs, and what
  * test_tracker.py:385-404 builds per frame on the serve path), with shape->input_dim == Cch + 2 and T = L*(F+1)

@@ -102,6 +102,8 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ntm_b200_finish": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "ntm_b200_set_profiling": (C.c_int32, [C.c_int32]),
+    "ntm_b200_zero_state": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ntm_b200_features_workspace_bytes": (C.c_int64, [C.POINTER(Shape), C.c_int64, C.c_int32, C.c_int32]),
     "ntm_b200_forward_seq_features": (C.c_int32, [C.POINTER(Shape), C.POINTER(Weights), C.c_void_p, C.c_int64, C.c_int32,
                                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(State),

@@ -13,6 +13,8 @@
 // Pure HBM-bound copies: one pass, coalesced (float2 where the row strides allow).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "ntm_b200.h"
 #include "ntm_b200_params.h"
 
@@ -55,6 +57,18 @@ __global__ void gather_kernel(const float* __restrict__ logits, float* __restric
   }
 }
 
+// zero_state (ntm_cell.py:284-315): M = tanh(var_M), w = sigmoid(var_w), read = tanh(var_read), one launch
+__global__ void zero_state_kernel(const float* __restrict__ vM, long long nM, const float* __restrict__ vw, long long nw,
+                                  const float* __restrict__ vr, long long nr, float* __restrict__ M, float* __restrict__ w,
+                                  float* __restrict__ r) {
+  const long long total = nM + nw + nr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < nM) M[i] = tanhf(vM[i]);
+    else if (i < nM + nw) w[i - nM] = 1.0f / (1.0f + expf(-vw[i - nM]));
+    else r[i - nM - nw] = tanhf(vr[i - nM - nw]);
+  }
+}
+
 }  // namespace io
 }  // namespace ntm_b200
 
@@ -88,6 +102,24 @@ extern "C" int32_t ntm_b200_gather_offsets(const float* logits, float* offsets, 
   }
   ntm_b200::io::gather_kernel<<<ntm_b200::B200_SMS, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, offsets, batch, frames, num_features, output_dim);
+  ntm_b200::count_launch();
+  return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
+}
+
+extern "C" int32_t ntm_b200_zero_state(const float* var_M, int64_t n_M, const float* var_w, int64_t n_w, const float* var_read,
+                                       int64_t n_read, float* M, float* w, float* read, void* stream) {
+  if (!var_M || !var_w || !var_read || !M || !w || !read) return NTM_B200_ERR_NULL_POINTER;
+  if (n_M < 1 || n_w < 1 || n_read < 1) return NTM_B200_ERR_BAD_SHAPE;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
+    cudaGetLastError();
+    return NTM_B200_ERR_NO_DEVICE;
+  }
+  const long long total = n_M + n_w + n_read;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 4ll * ntm_b200::B200_SMS);
+  ntm_b200::io::zero_state_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(var_M, n_M, var_w, n_w, var_read, n_read,
+                                                                                         M, w, read);
   ntm_b200::count_launch();
   return cudaGetLastError() == cudaSuccess ? NTM_B200_OK : NTM_B200_ERR_CUDA;
 }

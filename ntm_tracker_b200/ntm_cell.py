@@ -68,6 +68,7 @@ class NTMCell(object):
         self._dirty = True
         self._packed = None
         self._ws = {}
+        self._zero_ctrl = {}
         # validate the constructor arguments now, like _linear / circular_shift would
         # at graph-construction time (ValueError / AssertionError in the reference)
         self._check_shape(input_dim=1)
@@ -161,19 +162,36 @@ class NTMCell(object):
         """ntm_cell.py:284-315.  M = tanh(var), w = sigmoid(var) (NOT normalised),
         read = tanh(var), each shared by every sequence of the batch (stride-0
         views -- what tf.stack([M]*batch_size) expresses); controller_state zeros."""
-        names = [self.scope + "/init_state/" + n for n in ("M", "w", "read")]
-        self._create(names, self.input_dim or 1, initializer)
-        M = torch.tanh(self.variables[names[0]])
-        w = torch.sigmoid(self.variables[names[1]])
-        read = torch.tanh(self.variables[names[2]])
+        names = self.ensure_init_state(initializer)
+        vM, vw, vr = (self.variables[n] for n in names)
+        if self.device.type == "cuda":      # one launch of the library's own kernel (ntm_b200_zero_state)
+            M, w, read = torch.empty_like(vM), torch.empty_like(vw), torch.empty_like(vr)
+            with torch.cuda.device(self.device):
+                stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                _cabi.check(_cabi.load().ntm_b200_zero_state(
+                    vM.data_ptr(), vM.numel(), vw.data_ptr(), vw.numel(), vr.data_ptr(), vr.numel(),
+                    M.data_ptr(), w.data_ptr(), read.data_ptr(), stream), "zero_state")
+        else:                               # variables kept on the host (host-side logic tests; nothing can run there)
+            M, w, read = torch.tanh(vM), torch.sigmoid(vw), torch.tanh(vr)
         B = int(batch_size)
+        CL2 = 2 * self.controller_hidden_size * self.controller_num_layers
+        zc = self._zero_ctrl.get(B)
+        if zc is None:                      # read-only input of every call: one zero tensor per batch size
+            zc = self._zero_ctrl[B] = torch.zeros(B, CL2, device=self.device)
+            if len(self._zero_ctrl) > 8:
+                self._zero_ctrl = {B: zc}
         return {
             "M": M.unsqueeze(0).expand(B, -1, -1),
             "w": w.unsqueeze(0).expand(B, -1, -1),
             "read": read.unsqueeze(0).expand(B, -1, -1),
-            "controller_state": torch.zeros(
-                B, 2 * self.controller_hidden_size * self.controller_num_layers, device=self.device),
+            "controller_state": zc,
         }
+
+    def ensure_init_state(self, initializer=None):
+        """Create the three init_state variables if they do not exist yet; returns their names (M, w, read)."""
+        names = [self.scope + "/init_state/" + n for n in ("M", "w", "read")]
+        self._create(names, self.input_dim or 1, initializer)
+        return names
 
     def state_placeholder(self, batch_size):
         """ntm_cell.py:255-282: feedable state buffers (here: preallocated tensors)."""

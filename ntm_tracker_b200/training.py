@@ -105,7 +105,7 @@ class NTMTrainer(object):
             B, T, D = x.shape
             if cell.input_dim is None:
                 cell.build(D, self.tracker.initializer)
-            state = cell.zero_state(B, self.tracker.initializer)     # creates the init_state variables if missing
+            cell.ensure_init_state(self.tracker.initializer)          # before the variables are re-homed
             self._ensure_flat()
             gather = list(gather) if gather is not None else delimiter_steps(T, self.frame)
             N, M, R, W = cell.mem_size, cell.mem_dim, cell.read_head_size, cell.write_head_size
