@@ -121,13 +121,16 @@ class LoopNTMTracker(object):
             n = len(self._auto_bounds(T)) if (B * T * D * 4 >= (64 << 20) and T >= 16) else 1
         return max(1, min(int(n), T))
 
-    @staticmethod
-    def _auto_bounds(T):
+    first_cuts = (2, 8, 16)      # class attribute: ends of the first three blocks (experiments: LoopNTMTracker.first_cuts = ...)
+
+    @classmethod
+    def _auto_bounds(cls, T):
         """[0,2) [2,8) [8,16) [16,32) ... : only the first 2 steps' upload is not hidden behind kernels
         (blocks after the first are continuations, so short blocks cost next to nothing)."""
-        cuts = [0, min(2, T), min(8, T)]
-        if T > 8:
-            cuts.append(min(16, T))
+        c0, c1, c2 = cls.first_cuts
+        cuts = [0, min(c0, T), min(c1, T)]
+        if T > c1:
+            cuts.append(min(c2, T))
         while cuts[-1] < T:
             cuts.append(min(cuts[-1] + 16, T))
         cuts = sorted(set(cuts))

@@ -26,6 +26,8 @@ if os.environ.get("AB_SMI"):     # the bench's clock sampler, to see what it cos
     import subprocess
     smi = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader", "-lms", "100"],
                            stdout=subprocess.DEVNULL)
+if os.environ.get("AB_CUTS"):      # first block boundaries of the host pipeline, e.g. AB_CUTS=1,4,12
+    LoopNTMTracker.first_cuts = tuple(int(v) for v in os.environ["AB_CUTS"].split(","))
 for rep in range(2):
     for e in exps:
         os.environ["NTM_B200_EXP"] = e
