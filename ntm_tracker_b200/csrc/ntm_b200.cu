@@ -128,6 +128,7 @@ struct HostPlan {
   int nwarp, ctas_per_sm, tmem_cols;
   int max_teams;        // 2 when two CTAs share an SM (two decoupled teams), else 1
   int Gteam_max;        // resident sequences per team (upper bound, before the occupancy query)
+  bool resident_ok;     // false: the per-sequence state does not fit an 8-CTA cluster -- streaming mode only
   int smem_floats;
   int oMs, oW0, oW1, oCn, oScr, oSim, oSl, oWg, oK, oE, oA, oSm, oTc;
   int scr_floats;
@@ -220,7 +221,14 @@ int make_host_plan(const ntm_b200_shape* s, int nsm, int smem_optin, const EnvSw
       hp->variant = 0; hp->nwarp = 16; hp->ctas_per_sm = 1; hp->tmem_cols = 512; hp->max_teams = 1;
     }
   }
-  if (!ok) return NTM_B200_ERR_TOO_LARGE;
+  hp->resident_ok = ok;
+  if (!ok) {
+    // The persistent kernel cannot hold a sequence (N*M*4 beyond what 8 CTAs' shared memory takes).  The streaming
+    // kernels do not need that: such shapes run in streaming mode whatever the batch size (no debug taps there).
+    if (!stream_supported(s, nsm)) return NTM_B200_ERR_TOO_LARGE;
+    layout_for(s, 8, 16, 1 << 30, hp);      // shape-derived fields only (P, PO4, M4, ...); the carve-up is unused
+    hp->variant = 0; hp->nwarp = 16; hp->ctas_per_sm = 1; hp->tmem_cols = 512; hp->max_teams = 1;
+  }
   hp->Gteam_max = std::max(1, (nsm * hp->ctas_per_sm / hp->CS) / hp->max_teams);
   const int C = s->controller_hidden_size;
   for (int l = 0; l < s->controller_num_layers; ++l)
@@ -315,6 +323,10 @@ void layout_workspace(const ntm_b200_shape* s, const HostPlan& hp, long long B, 
                       Workspace* ws) {
   const int C = s->controller_hidden_size, L = s->controller_num_layers;
   const int Gm = hp.Gteam_max, NTm = hp.max_teams;
+  if (!hp.resident_ok) {      // streaming-only shape: the persistent kernel's workspace does not exist
+    *ws = Workspace{};
+    return;
+  }
   long long o = 0;
   auto take = [&](long long bytes) { long long r = o; o = align_up_ll(o + bytes, 256); return r; };
   ws->off_ctr = take(256);        // one counter per team, 128 B apart
@@ -373,6 +385,7 @@ int check_state(const ntm_b200_state* st) {
 // Execution mode for a call: 0 = persistent shared-memory-resident kernel, 1 = streaming (lockstep over
 // the whole shard, memory streamed from HBM).  NTM_B200_MODE=resident|stream overrides the choice.
 int choose_mode(const ntm_b200_shape* s, const HostPlan& hp, long long B, bool debug_taps, int nsm, const EnvSwitches& env) {
+  if (!hp.resident_ok) return 1;      // (make_host_plan made sure the streaming kernels cover the shape)
   if (debug_taps || !stream_supported(s, nsm)) return 0;
   if (env.mode >= 0) return env.mode;
   // resident: ceil(B / G) waves of ~30 us steps; streaming pays ~4 launches + GEMM weight loads per step
@@ -424,14 +437,21 @@ int32_t ntm_b200_query(const ntm_b200_shape* shape, int64_t batch, int64_t steps
   if (st) return st;
   Workspace ws{};
   layout_workspace(shape, hp, batch, steps, &ws);
-  plan_out->cluster_size = hp.CS;
-  plan_out->rows_per_cta = hp.NR;
   const int teams = (batch >= 2) ? hp.max_teams : 1;
-  plan_out->sequences_resident = (int32_t)std::min<long long>((long long)hp.Gteam_max * teams, batch);
+  if (hp.resident_ok) {
+    plan_out->cluster_size = hp.CS;
+    plan_out->rows_per_cta = hp.NR;
+    plan_out->sequences_resident = (int32_t)std::min<long long>((long long)hp.Gteam_max * teams, batch);
+    plan_out->smem_bytes_per_cta = 4ll * hp.smem_floats;
+  } else {      // streaming-only shape: there is no persistent-kernel geometry to report
+    plan_out->cluster_size = 0;
+    plan_out->rows_per_cta = 0;
+    plan_out->sequences_resident = 0;
+    plan_out->smem_bytes_per_cta = 0;
+  }
   plan_out->threads_per_cta = 32 * hp.nwarp;
   plan_out->ctas_per_sm = hp.ctas_per_sm;
   plan_out->teams = teams;
-  plan_out->smem_bytes_per_cta = 4ll * hp.smem_floats;
   StreamWorkspace sws{};
   stream_layout(shape, batch, steps, &sws);
   plan_out->workspace_bytes = std::max(ws.total, sws.total + 1024);
@@ -553,18 +573,20 @@ static int32_t forward_impl(const ntm_b200_shape* shape, const ntm_b200_weights*
   cudaError_t e;
   g_last_info[13] = mode;
 
+  if (!hp.resident_ok && debug_taps != nullptr) return NTM_B200_ERR_TOO_LARGE;   // taps come from the persistent kernel only
   const KernelVariant& kv = variant_of(hp);
   const int R = shape->read_head_size, W = shape->write_head_size;
-  const int smem_bytes = 4 * hp.smem_floats;
-  e = kv.set_smem(R, W, smem_bytes);
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(smem)");
-
-  // how many clusters are co-resident, split evenly over the teams
+  const int smem_bytes = hp.resident_ok ? 4 * hp.smem_floats : 0;
   const int nteams = (batch >= 2) ? hp.max_teams : 1;
-  int max_clusters = 0;
-  e = kv.max_clusters(R, W, hp.CS, hp.Gteam_max * hp.max_teams * hp.CS, smem_bytes, &max_clusters);
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveClusters");
-  if (max_clusters < nteams) return NTM_B200_ERR_TOO_LARGE;
+  int max_clusters = nteams;
+  if (mode == 0) {      // (the persistent kernel's launch geometry; the streaming mode configures its own kernels)
+    e = kv.set_smem(R, W, smem_bytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(smem)");
+    // how many clusters are co-resident, split evenly over the teams
+    e = kv.max_clusters(R, W, hp.CS, hp.Gteam_max * hp.max_teams * hp.CS, smem_bytes, &max_clusters);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveClusters");
+    if (max_clusters < nteams) return NTM_B200_ERR_TOO_LARGE;
+  }
   // Clusters per team.  Normally as many as there are sequences (up to what is co-resident).  When that would leave
   // each CTA more than 256 KiB of projection weights to stream per timestep -- batch 1, the serve path: one tracker,
   // 65 steps per frame, 10 MB of weights through two CTAs = 188 us per step -- every co-resident cluster is launched

@@ -91,6 +91,22 @@ def test_bad_shapes_are_rejected(lib, kw, code):
     assert st == code
 
 
+def test_streaming_only_shapes_are_accepted(lib, monkeypatch):
+    """A per-sequence state too large for the persistent kernel (N*M*4 beyond an 8-CTA cluster's shared memory) is
+    still a valid shape when the streaming kernels cover it: the query succeeds, reports no resident geometry, sizes
+    the workspace for the streaming mode, and the mode choice is "stream" at every batch size."""
+    monkeypatch.delenv("NTM_B200_MODE", raising=False)
+    shp = shape(mem_size=1024, mem_dim=512)
+    st, plan = query(lib, shp, 4, 8)
+    assert st == 0 and plan.cluster_size == 0 and plan.sequences_resident == 0 and plan.smem_bytes_per_cta == 0
+    assert plan.workspace_bytes > 4 * 8 * 800 * 4 and plan.packed_bytes > 0
+    m = C.c_int32(-1)
+    for B in (1, 64, 4096):
+        assert lib.ntm_b200_query_mode(C.byref(shp), B, C.byref(m)) == 0 and m.value == 1
+    monkeypatch.setenv("NTM_B200_MODE", "resident")       # cannot be forced into a kernel that cannot hold it
+    assert lib.ntm_b200_query_mode(C.byref(shp), 4, C.byref(m)) == 0 and m.value == 1
+
+
 def test_null_pointers_and_no_device(lib):
     plan = _cabi.Plan()
     assert lib.ntm_b200_query(None, 1, 1, C.byref(plan)) == 3

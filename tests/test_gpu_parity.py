@@ -555,3 +555,28 @@ def test_n128_register_addressing_variants(sr, W, R, wf, gemm_path):
     assert maxerr(to_np(st["M"]), rst["M"]) <= TOL
     w = to_np(st["w"])
     assert (w >= 0).all() and (w.sum(-1) < 1.0 + 1e-5).all()
+
+
+def test_streaming_only_shape_beyond_the_resident_planner():
+    """N = 1024, M = 512 (2 MiB per sequence) does not fit the persistent kernel's 8-CTA cluster; the library runs
+    it in streaming mode at any batch size instead of rejecting it."""
+    from ntm_tracker_b200 import _cabi
+    os.environ.pop("NTM_B200_MODE", None)
+    s = O.NTMShape(output_dim=2, input_dim=66, mem_size=1024, mem_dim=512, shift_range=1, controller_hidden_size=24,
+                   controller_num_layers=1, write_head_size=1, read_head_size=2)
+    params = O.init_params(s, 5, 0.2, random_biases=True)
+    B, T = 5, 3
+    x = np.random.RandomState(9).standard_normal((B, T, s.input_dim)).astype(np.float32)
+    trk = make_tracker(s, params, T)
+    out, logits = trk(torch.from_numpy(x).cuda())
+    trk.cell.finish()
+    assert _cabi.last_launch_info()["streaming"] == 1
+    _, rl, rst = O.run_sequence(params, s, x)
+    st = trk.final_state
+    assert maxerr(to_np(logits), rl) <= TOL
+    assert maxerr(to_np(st["w"]), rst["w"]) <= TOL
+    assert maxerr(to_np(st["read"]), rst["read"]) <= TOL
+    assert maxerr(to_np(st["M"]), rst["M"]) <= TOL
+    trk.cell.debug = True                       # debug taps exist in the persistent kernel only
+    with pytest.raises(ValueError):
+        trk(torch.from_numpy(x).cuda())
