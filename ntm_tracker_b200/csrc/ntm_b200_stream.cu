@@ -1443,7 +1443,9 @@ template <int R, int W, int CPL, bool FULLM>
 cudaError_t launch_tma_v(const MemArgs& a, long long B, int smem, cudaStream_t stream) {
   const bool n128 = a.N == 128 && a.S <= 7 && (R + W) <= TMA_NT / 32 && (a.sw_out & 3) == 0 &&
                     (reinterpret_cast<uintptr_t>(a.w_out) & 15) == 0 && a.NS == TMA_NS;
-  if (n128) return launch_tma_v2<R, W, CPL, FULLM, true, false>(a, B, smem, stream);
+  if constexpr (FULLM) {      // (instantiated for M = 128 / 256 / 512 only: every extra variant costs build time)
+    if (n128) return launch_tma_v2<R, W, CPL, FULLM, true, false>(a, B, smem, stream);
+  }
   if constexpr (CPL <= 2 && FULLM) {      // the 4-stage ring exists for M = 128 / 256 only (stages of >= 8 rows)
     if (a.NS == 4) return launch_tma_v2<R, W, CPL, FULLM, false, true>(a, B, smem, stream);
   }

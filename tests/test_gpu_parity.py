@@ -539,7 +539,7 @@ def test_n128_register_addressing_variants(sr, W, R, wf, gemm_path):
     """N = 128 takes the register-resident addressing path in both the streaming memory kernel and the persistent
     kernel (one warp per head, the circular shift by lane shuffles, compile-time tap counts 1 / 3 / 5 / 7): every
     shift range it covers, 1-3 write heads, write_first, against the fp64 oracle."""
-    s = O.NTMShape(output_dim=3, input_dim=20, mem_size=128, mem_dim=64, shift_range=sr, controller_hidden_size=24,
+    s = O.NTMShape(output_dim=3, input_dim=20, mem_size=128, mem_dim=128, shift_range=sr, controller_hidden_size=24,
                    controller_num_layers=1, write_head_size=W, read_head_size=R, write_first=wf)
     params = O.init_params(s, 11 + sr, 0.3, random_biases=True)      # large weights: peaky softmaxes and sharpening
     B, T = 7, 6
