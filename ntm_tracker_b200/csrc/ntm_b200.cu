@@ -136,7 +136,13 @@ struct HostPlan {
   long long packed_bytes, debug_floats;
 };
 
+// The 256-thread two-team build (ntm_b200_k256.cu) is a measured negative result: it is compiled only
+// with -DNTM_B200_WITH_K256 (NTM_B200_WITH_K256=1 for __graft_entry__.build()); without it NTM_B200_DUAL_TEAM is ignored.
+#ifdef NTM_B200_WITH_K256
 const KernelVariant& variant_of(const HostPlan& hp) { return hp.variant ? k256::variant() : k512::variant(); }
+#else
+const KernelVariant& variant_of(const HostPlan&) { return k512::variant(); }
+#endif
 
 int validate_shape(const ntm_b200_shape* s) {
   if (!s) return NTM_B200_ERR_NULL_POINTER;
@@ -207,7 +213,12 @@ int make_host_plan(const ntm_b200_shape* s, int nsm, int smem_optin, const EnvSw
   const int half_budget = std::min(smem_optin, B200_SMEM_SM / 2 - 1024 - 2048);   // slack for allocation granularity
   bool ok = false;
   // (tensor path only: with the SIMT GEMMs the two-team build is known to time out at 35 sequences per team)
-  if (env.dual_team && !env.disable_tc) {
+#ifdef NTM_B200_WITH_K256
+  const bool dual_team = env.dual_team;
+#else
+  const bool dual_team = false;
+#endif
+  if (dual_team && !env.disable_tc) {
     for (int CS = 1; CS <= 8 && !ok; CS *= 2) {
       if (layout_for(s, CS, 8, half_budget, hp)) {
         ok = true;
